@@ -1,0 +1,109 @@
+/*
+ * pwswarp.h -- C ABI of libpwswarp.so, the B200 (sm_100a) pixel-wise bilinear warp.
+ *
+ * This is the drop-in boundary for ONE path of mindazhao/PWStableNet: the
+ * torch.nn.functional.grid_sample calls that resample each unstable frame by the
+ * per-pixel map netG produced (R = the reference checkout):
+ *     R/main_new.py:106,109,116,118   training warps, RGB x3 stages x2 clips + gray
+ *     R/main_new.py:197               chained affine warp (gradient flows to the frame)
+ *     R/main_new.py:716               inference warp at native video resolution
+ *     R/main.py:106,107,114,115,319,325,643   the stale twins
+ *     R/main_new.py:214               loss_g.backward() -> grid_sampler_2d_backward
+ * What sits underneath those calls in the reference is ATen:
+ *     aten::grid_sampler_2d(Tensor input, Tensor grid, int interpolation_mode,
+ *                           int padding_mode, bool align_corners) -> Tensor
+ *     aten::grid_sampler_2d_backward(Tensor grad_output, Tensor input, Tensor grid, int, int, bool,
+ *                           bool[2] output_mask) -> (Tensor, Tensor)
+ * ($TORCH/include/ATen/native/cuda/GridSampler.h:12-24 is the launcher pair the
+ * two entry points below replace.)  Enumerations are numerically identical to
+ * ATen's (GridSamplerUtils.h:14-15).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types, no C++ exceptions across the ABI
+ *   - every buffer is caller-owned DEVICE memory; the library never allocates,
+ *     frees or retains a pointer past the call
+ *   - strides are in ELEMENTS and arbitrary (permuted / sliced views are the norm:
+ *     the reference passes planar-stored maps, strides (2HW, W, 1, HW))
+ *   - asynchronous on `stream` (a cudaStream_t; NULL = legacy default stream)
+ *   - return 0 on success, negative pws_status on failure; the message is in the
+ *     thread-local pws_last_error()
+ *   - stateless and re-entrant
+ */
+#ifndef PWSWARP_H_
+#define PWSWARP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PWS_ABI_VERSION 1
+
+typedef enum pws_dtype {
+    PWS_F32 = 0,
+    PWS_F16 = 1,
+    PWS_BF16 = 2,
+    PWS_F64 = 3,
+    PWS_U8 = 4,
+    PWS_I32 = 5
+} pws_dtype;
+
+typedef enum pws_status {
+    PWS_OK = 0,
+    PWS_EINVAL = -1,       /* bad shape / stride / pointer / enum: ValueError-class */
+    PWS_EUNSUPPORTED = -2, /* valid for torch, outside this library's scope */
+    PWS_ECUDA = -3         /* a CUDA runtime call failed */
+} pws_status;
+
+/* ATen GridSamplerInterpolation / GridSamplerPadding */
+enum { PWS_INTERP_BILINEAR = 0, PWS_INTERP_NEAREST = 1, PWS_INTERP_BICUBIC = 2 };
+enum { PWS_PAD_ZEROS = 0, PWS_PAD_BORDER = 1, PWS_PAD_REFLECTION = 2 };
+
+/* A 4-D strided view of device memory.
+ *   frames / outputs / grad_output / grad_input : (N, C, H, W)
+ *   maps  / grad_grid                            : (N, H_out, W_out, 2)   [..., 0] = x, [..., 1] = y */
+typedef struct pws_tensor {
+    void *data;
+    int32_t dtype;  /* pws_dtype */
+    int32_t device; /* CUDA ordinal the memory lives on */
+    int64_t size[4];
+    int64_t stride[4];
+} pws_tensor;
+
+int pws_abi_version(void);
+
+/* Thread-local, valid until the next failing call on the same thread. */
+const char *pws_last_error(void);
+
+/* out[n,c,h,w] = sum over the 4 bilinear taps of in[n,c,y_tap,x_tap] * w_tap,
+ * replaces aten::grid_sampler_2d for interp = bilinear, padding in {zeros, border}.
+ * Frame dtype: f32, f16, bf16, f64.  Map dtype: the frame's dtype or f32 (an
+ * extension torch does not offer: 16-bit frames with fp32 maps, BASELINE config 5).
+ * `out` has the frame dtype; arithmetic is fp32 (fp64 for f64), in ATen's CUDA
+ * operation order, so fp32 results are bit-identical to torch's CUDA kernel. */
+int pws_warp2d_forward(const pws_tensor *in, const pws_tensor *grid, pws_tensor *out,
+                       int interp, int padding, int align_corners, void *stream);
+
+/* Replaces aten::grid_sampler_2d_backward.  gin / ggrid may be NULL
+ * (== output_mask[0] / [1] false).  gin must be a dense (N,C,H,W)-contiguous
+ * buffer; it does NOT need to arrive zeroed: the library zero-fills it itself,
+ * frame by frame, just ahead of the scatter so the lines are still in L2 when
+ * the atomics land (DESIGN.md "backward").  ggrid is fully overwritten. */
+int pws_warp2d_backward(const pws_tensor *gout, const pws_tensor *in, const pws_tensor *grid,
+                        pws_tensor *gin, pws_tensor *ggrid,
+                        int interp, int padding, int align_corners, void *stream);
+
+/* Debug / parity entry: the north-west tap (x0, y0), the 4-bit validity mask
+ * (bit0 nw, bit1 ne, bit2 sw, bit3 se) and optionally the four weights the forward
+ * pass uses for every output pixel.  x0, y0: int32 (N,Ho,Wo) contiguous; mask: uint8
+ * (N,Ho,Wo) contiguous; weights: float (N,Ho,Wo,4) contiguous or NULL.
+ * grid must be f32. */
+int pws_warp2d_taps(const pws_tensor *grid, int64_t in_h, int64_t in_w,
+                    int32_t *x0, int32_t *y0, uint8_t *mask, float *weights,
+                    int padding, int align_corners, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PWSWARP_H_ */

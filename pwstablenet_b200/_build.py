@@ -1,0 +1,68 @@
+"""Builds libpwswarp.so in-tree with nvcc for sm_100a (no JIT cache: the built
+library travels with the repository snapshot to the GPU box)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libpwswarp.so")
+SOURCES = ["capi.cu", "warp_fwd.cu", "warp_bwd.cu"]
+HEADERS = ["pws_common.cuh", os.path.join("..", "..", "include", "pwswarp.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-cudart", "shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (need CUDA 12.9 for sm_100a)")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into pwstablenet_b200/libpwswarp.so. Returns the path."""
+    if not force and not _stale():
+        return LIB
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    objs = []
+    for s in SOURCES:
+        obj = os.path.join(objdir, s.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
+    link = [nvcc, "-shared", "-cudart", "shared", "-o", LIB, *objs,
+            "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    subprocess.check_call(link)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_library(force="-f" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,78 @@
+"""ctypes binding of libpwswarp.so (include/pwswarp.h).  There is no fallback:
+if the CUDA library is missing or does not load, importing the ops fails loudly."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpwswarp.so")
+
+PWS_F32, PWS_F16, PWS_BF16, PWS_F64, PWS_U8, PWS_I32 = range(6)
+PWS_OK, PWS_EINVAL, PWS_EUNSUPPORTED, PWS_ECUDA = 0, -1, -2, -3
+ABI_VERSION = 1
+
+EXPORTS = (
+    "pws_abi_version",
+    "pws_last_error",
+    "pws_warp2d_forward",
+    "pws_warp2d_backward",
+    "pws_warp2d_taps",
+)
+
+
+class PwsTensor(ctypes.Structure):
+    _fields_ = [
+        ("data", ctypes.c_void_p),
+        ("dtype", ctypes.c_int32),
+        ("device", ctypes.c_int32),
+        ("size", ctypes.c_int64 * 4),
+        ("stride", ctypes.c_int64 * 4),
+    ]
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libpwswarp.so (built by pwstablenet_b200._build.build_library / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"pwstablenet_b200: {LIB_PATH} is missing. Build it with "
+            "`python -m pwstablenet_b200._build` (needs nvcc 12.9); there is no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    P = ctypes.POINTER(PwsTensor)
+    lib.pws_abi_version.restype = ctypes.c_int
+    lib.pws_last_error.restype = ctypes.c_char_p
+    lib.pws_warp2d_forward.restype = ctypes.c_int
+    lib.pws_warp2d_forward.argtypes = [P, P, P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.pws_warp2d_backward.restype = ctypes.c_int
+    lib.pws_warp2d_backward.argtypes = [P, P, P, P, P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.pws_warp2d_taps.restype = ctypes.c_int
+    lib.pws_warp2d_taps.argtypes = [P, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    got = lib.pws_abi_version()
+    if got != ABI_VERSION:
+        raise RuntimeError(f"pwstablenet_b200: libpwswarp.so has ABI {got}, expected {ABI_VERSION}; rebuild it")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().pws_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    """Turn a pws_status into the exception torch would have raised."""
+    if rc == PWS_OK:
+        return
+    msg = last_error()
+    if rc == PWS_EINVAL:
+        raise RuntimeError(msg)  # torch raises RuntimeError for TORCH_CHECK failures
+    if rc == PWS_EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"pwswarp CUDA error: {msg}")

@@ -1,0 +1,259 @@
+// capi.cu -- extern "C" boundary of libpwswarp.so (include/pwswarp.h).
+// Validation mirrors check_grid_sampler_common / check_grid_sampler_2d
+// ($TORCH/include/ATen/native/GridSamplerUtils.h:23-71); messages keep ATen's
+// "grid_sampler(): ..." wording so the Python shim can re-raise them verbatim.
+#include "pws_common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+
+namespace pws {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+int elem_size(int dt)
+{
+    switch (dt) {
+        case PWS_F32: return 4;
+        case PWS_F16: case PWS_BF16: return 2;
+        case PWS_F64: return 8;
+        case PWS_U8: return 1;
+        case PWS_I32: return 4;
+        default: return 0;
+    }
+}
+
+// extent (in elements) one batch item of `t` spans, over dims 1..3
+int64_t item_span(const pws_tensor *t)
+{
+    int64_t s = 1;
+    for (int d = 1; d < 4; ++d) {
+        if (t->size[d] == 0) return 0;
+        const int64_t st = t->stride[d] < 0 ? -t->stride[d] : t->stride[d];
+        s += (t->size[d] - 1) * st;
+    }
+    return s;
+}
+
+int make_view(const pws_tensor *t, const char *what, View *v)
+{
+    if (!t) { set_error("%s: null tensor descriptor", what); return PWS_EINVAL; }
+    if (elem_size(t->dtype) == 0) { set_error("%s: unknown dtype %d", what, t->dtype); return PWS_EINVAL; }
+    for (int d = 0; d < 4; ++d) {
+        if (t->size[d] < 0) { set_error("%s: negative size", what); return PWS_EINVAL; }
+        if (t->stride[d] < 0) { set_error("%s: negative strides are not supported", what); return PWS_EUNSUPPORTED; }
+        if (t->size[d] > INT_MAX) { set_error("%s: dimension %d too large", what, d); return PWS_EUNSUPPORTED; }
+    }
+    if (item_span(t) >= ((int64_t)1 << 31)) {
+        set_error("%s: one batch item spans >= 2^31 elements (32-bit in-frame offsets)", what);
+        return PWS_EUNSUPPORTED;
+    }
+    const int64_t numel = t->size[0] * t->size[1] * t->size[2] * t->size[3];
+    if (numel > 0 && !t->data) { set_error("%s: null data pointer", what); return PWS_EINVAL; }
+    v->p = t->data;
+    v->sN = t->stride[0];
+    v->s1 = (int32_t)t->stride[1];
+    v->s2 = (int32_t)t->stride[2];
+    v->s3 = (int32_t)t->stride[3];
+    return PWS_OK;
+}
+
+int check_modes(int interp, int padding)
+{
+    if (interp < 0 || interp > 2) { set_error("grid_sampler(): invalid interpolation mode %d", interp); return PWS_EINVAL; }
+    if (padding < 0 || padding > 2) { set_error("grid_sampler(): invalid padding mode %d", padding); return PWS_EINVAL; }
+    if (interp != PWS_INTERP_BILINEAR) {
+        set_error("pwswarp: only mode='bilinear' is implemented (got interpolation_mode=%d)", interp);
+        return PWS_EUNSUPPORTED;
+    }
+    if (padding == PWS_PAD_REFLECTION) {
+        set_error("pwswarp: padding_mode='reflection' is not implemented (zeros and border only)");
+        return PWS_EUNSUPPORTED;
+    }
+    return PWS_OK;
+}
+
+int check_pair(const pws_tensor *in, const pws_tensor *grid)
+{
+    if (!in || !grid) { set_error("grid_sampler(): expected input and grid to not be undefined"); return PWS_EINVAL; }
+    if (in->device != grid->device) {
+        set_error("grid_sampler(): expected input and grid to be on same device, but input is on cuda:%d and grid is on cuda:%d",
+                  in->device, grid->device);
+        return PWS_EINVAL;
+    }
+    if (in->size[0] != grid->size[0]) {
+        set_error("grid_sampler(): expected grid and input to have same batch size, but got input with sizes [%lld, %lld, %lld, %lld] and grid with sizes [%lld, %lld, %lld, %lld]",
+                  (long long)in->size[0], (long long)in->size[1], (long long)in->size[2], (long long)in->size[3],
+                  (long long)grid->size[0], (long long)grid->size[1], (long long)grid->size[2], (long long)grid->size[3]);
+        return PWS_EINVAL;
+    }
+    if (grid->size[3] != 2) {
+        set_error("grid_sampler(): expected grid to have size 2 in last dimension, but got grid with sizes [%lld, %lld, %lld, %lld]",
+                  (long long)grid->size[0], (long long)grid->size[1], (long long)grid->size[2], (long long)grid->size[3]);
+        return PWS_EINVAL;
+    }
+    for (int d = 2; d < 4; ++d)
+        if (in->size[d] <= 0) {
+            set_error("grid_sampler(): expected input to have non-empty spatial dimensions, but input has sizes [%lld, %lld, %lld, %lld] with dimension %d being empty",
+                      (long long)in->size[0], (long long)in->size[1], (long long)in->size[2], (long long)in->size[3], d);
+            return PWS_EINVAL;
+        }
+    return PWS_OK;
+}
+
+int fill_geometry(const pws_tensor *in, const pws_tensor *grid, int padding, int align, Geometry *g)
+{
+    g->N = (int32_t)in->size[0]; g->C = (int32_t)in->size[1];
+    g->H = (int32_t)in->size[2]; g->W = (int32_t)in->size[3];
+    g->Ho = (int32_t)grid->size[1]; g->Wo = (int32_t)grid->size[2];
+    g->padding = padding; g->align = align ? 1 : 0;
+    return PWS_OK;
+}
+
+int same_shape(const pws_tensor *t, int64_t a, int64_t b, int64_t c, int64_t d, const char *what)
+{
+    if (t->size[0] != a || t->size[1] != b || t->size[2] != c || t->size[3] != d) {
+        set_error("%s: expected sizes [%lld, %lld, %lld, %lld], got [%lld, %lld, %lld, %lld]", what,
+                  (long long)a, (long long)b, (long long)c, (long long)d,
+                  (long long)t->size[0], (long long)t->size[1], (long long)t->size[2], (long long)t->size[3]);
+        return PWS_EINVAL;
+    }
+    return PWS_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int finish(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e)); return PWS_ECUDA; }
+    return PWS_OK;
+}
+
+}  // namespace
+}  // namespace pws
+
+using namespace pws;
+
+#define PWS_TRY(expr) do { int rc_ = (expr); if (rc_ != PWS_OK) return rc_; } while (0)
+
+extern "C" {
+
+__attribute__((visibility("default"))) int pws_abi_version(void) { return PWS_ABI_VERSION; }
+
+__attribute__((visibility("default"))) const char *pws_last_error(void) { return g_err; }
+
+__attribute__((visibility("default")))
+int pws_warp2d_forward(const pws_tensor *in, const pws_tensor *grid, pws_tensor *out,
+                       int interp, int padding, int align_corners, void *stream)
+{
+    PWS_TRY(check_modes(interp, padding));
+    PWS_TRY(check_pair(in, grid));
+    if (!out) { set_error("forward: null output descriptor"); return PWS_EINVAL; }
+    Problem pb{};
+    PWS_TRY(make_view(in, "input", &pb.in));
+    PWS_TRY(make_view(grid, "grid", &pb.grid));
+    PWS_TRY(make_view(out, "output", &pb.out));
+    PWS_TRY(same_shape(out, in->size[0], in->size[1], grid->size[1], grid->size[2], "output"));
+    if (out->dtype != in->dtype) { set_error("output: dtype must equal the input's"); return PWS_EINVAL; }
+    if (out->device != in->device) { set_error("output: must be on the input's device"); return PWS_EINVAL; }
+    fill_geometry(in, grid, padding, align_corners, &pb.g);
+    pb.in_dtype = in->dtype; pb.grid_dtype = grid->dtype;
+    if ((int64_t)pb.g.N * pb.g.C * pb.g.Ho * pb.g.Wo == 0) return PWS_OK;
+    DeviceGuard dg(in->device);
+    if (!dg.ok) { set_error("forward: cannot select cuda:%d", in->device); return PWS_ECUDA; }
+    PWS_TRY(launch_forward(pb, (cudaStream_t)stream));
+    return finish("forward");
+}
+
+__attribute__((visibility("default")))
+int pws_warp2d_backward(const pws_tensor *gout, const pws_tensor *in, const pws_tensor *grid,
+                        pws_tensor *gin, pws_tensor *ggrid,
+                        int interp, int padding, int align_corners, void *stream)
+{
+    PWS_TRY(check_modes(interp, padding));
+    PWS_TRY(check_pair(in, grid));
+    if (!gout) { set_error("backward: null grad_output descriptor"); return PWS_EINVAL; }
+    Problem pb{};
+    PWS_TRY(make_view(in, "input", &pb.in));
+    PWS_TRY(make_view(grid, "grid", &pb.grid));
+    PWS_TRY(make_view(gout, "grad_output", &pb.gout));
+    PWS_TRY(same_shape(gout, in->size[0], in->size[1], grid->size[1], grid->size[2], "grad_output"));
+    if (gout->dtype != in->dtype) { set_error("grad_output: dtype must equal the input's"); return PWS_EINVAL; }
+    if (gout->device != in->device) { set_error("grad_output: must be on the input's device"); return PWS_EINVAL; }
+    pb.want_gin = gin != nullptr;
+    pb.want_ggrid = ggrid != nullptr;
+    if (gin) {
+        PWS_TRY(make_view(gin, "grad_input", &pb.gin));
+        PWS_TRY(same_shape(gin, in->size[0], in->size[1], in->size[2], in->size[3], "grad_input"));
+        if (gin->dtype != in->dtype || gin->device != in->device) { set_error("grad_input: dtype/device must equal the input's"); return PWS_EINVAL; }
+        const int64_t C = in->size[1], H = in->size[2], W = in->size[3];
+        const bool dense = gin->stride[3] == 1 && gin->stride[2] == W && gin->stride[1] == H * W &&
+                           (gin->stride[0] == C * H * W || in->size[0] <= 1);
+        if (!dense) { set_error("grad_input: must be (N,C,H,W)-contiguous (the library zero-fills it)"); return PWS_EINVAL; }
+        pb.gin.sN = C * H * W;
+    }
+    if (ggrid) {
+        PWS_TRY(make_view(ggrid, "grad_grid", &pb.ggrid));
+        PWS_TRY(same_shape(ggrid, grid->size[0], grid->size[1], grid->size[2], 2, "grad_grid"));
+        if (ggrid->dtype != grid->dtype || ggrid->device != in->device) { set_error("grad_grid: dtype/device must equal the grid's"); return PWS_EINVAL; }
+    }
+    fill_geometry(in, grid, padding, align_corners, &pb.g);
+    pb.in_dtype = in->dtype; pb.grid_dtype = grid->dtype;
+    DeviceGuard dg(in->device);
+    if (!dg.ok) { set_error("backward: cannot select cuda:%d", in->device); return PWS_ECUDA; }
+    if (pb.g.N == 0) return PWS_OK;
+    if ((int64_t)pb.g.C * pb.g.Ho * pb.g.Wo == 0) {
+        // nothing scatters; grad_input is still defined (all zeros)
+        if (gin && (int64_t)pb.g.C * pb.g.H * pb.g.W > 0) {
+            cudaError_t e = cudaMemsetAsync(gin->data, 0, (size_t)(in->size[0] * pb.gin.sN * elem_size(in->dtype)), (cudaStream_t)stream);
+            if (e != cudaSuccess) { set_error("backward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return PWS_ECUDA; }
+        }
+        return PWS_OK;
+    }
+    PWS_TRY(launch_backward(pb, (cudaStream_t)stream));
+    return finish("backward");
+}
+
+__attribute__((visibility("default")))
+int pws_warp2d_taps(const pws_tensor *grid, int64_t in_h, int64_t in_w,
+                    int32_t *x0, int32_t *y0, uint8_t *mask, float *weights,
+                    int padding, int align_corners, void *stream)
+{
+    PWS_TRY(check_modes(PWS_INTERP_BILINEAR, padding));
+    if (!grid || !x0 || !y0 || !mask) { set_error("taps: null argument"); return PWS_EINVAL; }
+    if (grid->dtype != PWS_F32) { set_error("taps: grid must be f32"); return PWS_EUNSUPPORTED; }
+    if (grid->size[3] != 2) { set_error("taps: grid must have size 2 in its last dimension"); return PWS_EINVAL; }
+    if (in_h <= 0 || in_w <= 0 || in_h > INT_MAX || in_w > INT_MAX) { set_error("taps: bad frame size"); return PWS_EINVAL; }
+    View gv;
+    PWS_TRY(make_view(grid, "grid", &gv));
+    Geometry g{};
+    g.N = (int32_t)grid->size[0]; g.C = 1; g.H = (int32_t)in_h; g.W = (int32_t)in_w;
+    g.Ho = (int32_t)grid->size[1]; g.Wo = (int32_t)grid->size[2];
+    g.padding = padding; g.align = align_corners ? 1 : 0;
+    DeviceGuard dg(grid->device);
+    if (!dg.ok) { set_error("taps: cannot select cuda:%d", grid->device); return PWS_ECUDA; }
+    PWS_TRY(launch_taps(gv, g, x0, y0, mask, weights, (cudaStream_t)stream));
+    return finish("taps");
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+"""Drop-in for the reference's warp calls: same Python signature as
+torch.nn.functional.grid_sample ($TORCH/nn/functional.py:5085-5242), executed by
+the hand-written sm_100a kernels behind libpwswarp.so.
+
+Reference call sites served (R = the PWStableNet checkout):
+    R/main_new.py:106,116   functional.grid_sample((rgb + 1) * 127.5, grid1[nl])
+    R/main_new.py:109,118   gray warps
+    R/main_new.py:197       functional.grid_sample(fake2[nl], affine_grid(...))  (grad -> frame)
+    R/main_new.py:716       functional.grid_sample(now, grid_resize)              (inference)
+All of them pass (input, grid) positionally and leave the keywords at their defaults.
+
+CUDA tensors only: a CPU tensor raises (no CPU fallback, no multi-backend dispatch).
+"""
+from __future__ import annotations
+
+import ctypes
+import warnings
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_DTYPES = {
+    torch.float32: _lib.PWS_F32,
+    torch.float16: _lib.PWS_F16,
+    torch.bfloat16: _lib.PWS_BF16,
+    torch.float64: _lib.PWS_F64,
+}
+_INTERP = {"bilinear": 0, "nearest": 1, "bicubic": 2}
+_PADDING = {"zeros": 0, "border": 1, "reflection": 2}
+
+
+def _desc(t: torch.Tensor) -> _lib.PwsTensor:
+    d = _lib.PwsTensor()
+    d.data = t.data_ptr()
+    d.dtype = _DTYPES[t.dtype]
+    d.device = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    for i in range(4):
+        d.size[i] = t.size(i)
+        d.stride[i] = t.stride(i)
+    return d
+
+
+def _stream(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(input: torch.Tensor, grid: torch.Tensor) -> None:
+    if not (input.is_cuda and grid.is_cuda):
+        raise RuntimeError(
+            "pwstablenet_b200.grid_sample runs on CUDA tensors only (input on "
+            f"{input.device}, grid on {grid.device}); there is no CPU fallback"
+        )
+    if input.device != grid.device:
+        raise RuntimeError(
+            "grid_sampler(): expected input and grid to be on same device, but input "
+            f"is on {input.device} and grid is on {grid.device}"
+        )
+    if input.dim() != 4 or grid.dim() != 4:
+        if input.dim() == 5 and grid.dim() == 5:
+            raise NotImplementedError("pwstablenet_b200.grid_sample: 5-D (volumetric) sampling is out of scope")
+        raise RuntimeError(
+            "grid_sampler(): expected 4D input and grid with same number of dimensions, but got "
+            f"input with sizes {list(input.shape)} and grid with sizes {list(grid.shape)}"
+        )
+    if input.dtype not in _DTYPES:
+        raise NotImplementedError(f"pwstablenet_b200.grid_sample: unsupported frame dtype {input.dtype}")
+    if grid.dtype != input.dtype and not (grid.dtype == torch.float32 and input.dtype in (torch.float16, torch.bfloat16)):
+        raise RuntimeError(
+            f"grid_sampler(): expected input and grid to have same dtype, but input has {input.dtype} "
+            f"and grid has {grid.dtype} (extension: fp32 maps are accepted with fp16/bf16 frames)"
+        )
+
+
+def warp2d_forward(input: torch.Tensor, grid: torch.Tensor, padding: int, align_corners: bool) -> torch.Tensor:
+    """aten::grid_sampler_2d replacement (bilinear). Returns an NCHW-contiguous tensor, as ATen does."""
+    lib = _lib.load()
+    N, C = input.size(0), input.size(1)
+    out = torch.empty((N, C, grid.size(1), grid.size(2)), dtype=input.dtype, device=input.device)
+    with torch.cuda.device_of(input):
+        rc = lib.pws_warp2d_forward(ctypes.byref(_desc(input)), ctypes.byref(_desc(grid)), ctypes.byref(_desc(out)),
+                                    0, padding, int(align_corners), _stream(input))
+    _lib.check(rc)
+    return out
+
+
+def _like_layout(t: torch.Tensor) -> torch.Tensor:
+    """Uninitialised tensor with t's sizes; keeps t's strides when they are dense (the
+    reference's maps are planar-stored permuted views), otherwise contiguous."""
+    expected, dense = 1, t.numel() > 0
+    for st, sz in sorted(zip(t.stride(), t.size())):
+        if sz != 1:
+            dense = dense and st == expected
+            expected *= sz
+    if dense:
+        return torch.empty_strided(t.size(), t.stride(), dtype=t.dtype, device=t.device)
+    return torch.empty(t.size(), dtype=t.dtype, device=t.device)
+
+
+def warp2d_backward(grad_output: torch.Tensor, input: torch.Tensor, grid: torch.Tensor, padding: int,
+                    align_corners: bool, output_mask=(True, True)):
+    """aten::grid_sampler_2d_backward replacement. Returns (grad_input | None, grad_grid | None)."""
+    lib = _lib.load()
+    if grid.dtype != input.dtype:
+        raise NotImplementedError("pwstablenet_b200: backward needs the map in the frame's dtype")
+    gin = torch.empty(input.size(), dtype=input.dtype, device=input.device) if output_mask[0] else None
+    ggrid = _like_layout(grid) if output_mask[1] else None
+    with torch.cuda.device_of(input):
+        rc = lib.pws_warp2d_backward(
+            ctypes.byref(_desc(grad_output)), ctypes.byref(_desc(input)), ctypes.byref(_desc(grid)),
+            ctypes.byref(_desc(gin)) if gin is not None else None,
+            ctypes.byref(_desc(ggrid)) if ggrid is not None else None,
+            0, padding, int(align_corners), _stream(input))
+    _lib.check(rc)
+    return gin, ggrid
+
+
+class _Warp2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, grid, padding, align_corners):
+        ctx.save_for_backward(input, grid)
+        ctx.padding = padding
+        ctx.align_corners = align_corners
+        return warp2d_forward(input, grid, padding, align_corners)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        input, grid = ctx.saved_tensors
+        mask = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        gin, ggrid = warp2d_backward(grad_output, input, grid, ctx.padding, ctx.align_corners, mask)
+        return gin, ggrid, None, None
+
+
+def grid_sample(input: torch.Tensor, grid: torch.Tensor, mode: str = "bilinear", padding_mode: str = "zeros",
+                align_corners: Optional[bool] = None) -> torch.Tensor:
+    """Same contract as torch.nn.functional.grid_sample for 4-D CUDA tensors,
+    mode='bilinear', padding_mode in {'zeros', 'border'}."""
+    if mode not in _INTERP:
+        raise ValueError(
+            f"nn.functional.grid_sample(): expected mode to be 'bilinear', 'nearest' or 'bicubic', but got: '{mode}'")
+    if padding_mode not in _PADDING:
+        raise ValueError(
+            "nn.functional.grid_sample(): expected padding_mode to be 'zeros', 'border', or 'reflection', "
+            f"but got: '{padding_mode}'")
+    if mode != "bilinear":
+        raise NotImplementedError(f"pwstablenet_b200.grid_sample: mode='{mode}' is out of scope (bilinear only)")
+    if padding_mode == "reflection":
+        raise NotImplementedError("pwstablenet_b200.grid_sample: padding_mode='reflection' is out of scope")
+    if align_corners is None:
+        warnings.warn(
+            "Default grid_sample and affine_grid behavior has changed to align_corners=False since 1.3.0. "
+            "Please specify align_corners=True if the old behavior is desired. "
+            "See the documentation of grid_sample for details.")
+        align_corners = False
+    _require_cuda(input, grid)
+    return _Warp2d.apply(input, grid, _PADDING[padding_mode], bool(align_corners))
+
+
+def warp_taps(grid: torch.Tensor, in_h: int, in_w: int, padding_mode: str = "zeros", align_corners: bool = False,
+              want_weights: bool = True):
+    """Debug/parity: north-west tap indices, validity mask and weights the forward pass uses."""
+    lib = _lib.load()
+    if not grid.is_cuda or grid.dtype != torch.float32 or grid.dim() != 4:
+        raise RuntimeError("warp_taps: grid must be a 4-D float32 CUDA tensor")
+    N, Ho, Wo, _ = grid.shape
+    x0 = torch.empty((N, Ho, Wo), dtype=torch.int32, device=grid.device)
+    y0 = torch.empty_like(x0)
+    mask = torch.empty((N, Ho, Wo), dtype=torch.uint8, device=grid.device)
+    wts = torch.empty((N, Ho, Wo, 4), dtype=torch.float32, device=grid.device) if want_weights else None
+    with torch.cuda.device_of(grid):
+        rc = lib.pws_warp2d_taps(ctypes.byref(_desc(grid)), in_h, in_w, x0.data_ptr(), y0.data_ptr(), mask.data_ptr(),
+                                 wts.data_ptr() if wts is not None else None, _PADDING[padding_mode],
+                                 int(align_corners), _stream(grid))
+    _lib.check(rc)
+    return x0, y0, mask, wts
+
+
+_torch_grid_sample = None
+
+
+def install() -> None:
+    """Route torch.nn.functional.grid_sample to this implementation so the reference's
+    main_new.py / main.py run unmodified (they call `functional.grid_sample(...)` /
+    `F.grid_sample(...)` through the module attribute)."""
+    global _torch_grid_sample
+    import torch.nn.functional as F
+    _lib.load()
+    if _torch_grid_sample is None:
+        _torch_grid_sample = F.grid_sample
+        F.grid_sample = grid_sample
+
+
+def uninstall() -> None:
+    global _torch_grid_sample
+    import torch.nn.functional as F
+    if _torch_grid_sample is not None:
+        F.grid_sample = _torch_grid_sample
+        _torch_grid_sample = None
