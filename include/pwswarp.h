@@ -76,6 +76,10 @@ int pws_abi_version(void);
 /* Thread-local, valid until the next failing call on the same thread. */
 const char *pws_last_error(void);
 
+/* Number of CUDA kernels this library has launched in this process (all threads).
+ * bench.py reports the difference over its timed region as "gpu_launches". */
+uint64_t pws_launch_count(void);
+
 /* out[n,c,h,w] = sum over the 4 bilinear taps of in[n,c,y_tap,x_tap] * w_tap,
  * replaces aten::grid_sampler_2d for interp = bilinear, padding in {zeros, border}.
  * Frame dtype: f32, f16, bf16, f64.  Map dtype: the frame's dtype or f32 (an

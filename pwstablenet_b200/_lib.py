@@ -15,6 +15,7 @@ ABI_VERSION = 1
 EXPORTS = (
     "pws_abi_version",
     "pws_last_error",
+    "pws_launch_count",
     "pws_warp2d_forward",
     "pws_warp2d_backward",
     "pws_warp2d_taps",
@@ -48,6 +49,7 @@ def load() -> ctypes.CDLL:
     P = ctypes.POINTER(PwsTensor)
     lib.pws_abi_version.restype = ctypes.c_int
     lib.pws_last_error.restype = ctypes.c_char_p
+    lib.pws_launch_count.restype = ctypes.c_uint64
     lib.pws_warp2d_forward.restype = ctypes.c_int
     lib.pws_warp2d_forward.argtypes = [P, P, P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.pws_warp2d_backward.restype = ctypes.c_int
@@ -60,6 +62,11 @@ def load() -> ctypes.CDLL:
         raise RuntimeError(f"pwstablenet_b200: libpwswarp.so has ABI {got}, expected {ABI_VERSION}; rebuild it")
     _lib = lib
     return lib
+
+
+def launch_count() -> int:
+    """Kernels launched by libpwswarp.so so far in this process."""
+    return int(load().pws_launch_count())
 
 
 def last_error() -> str:

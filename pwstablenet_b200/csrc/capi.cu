@@ -4,12 +4,16 @@
 // "grid_sampler(): ..." wording so the Python shim can re-raise them verbatim.
 #include "pws_common.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
 namespace pws {
 
 static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void note_launch(int kernels) { g_launches.fetch_add((uint64_t)kernels, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...)
 {
@@ -161,6 +165,8 @@ extern "C" {
 __attribute__((visibility("default"))) int pws_abi_version(void) { return PWS_ABI_VERSION; }
 
 __attribute__((visibility("default"))) const char *pws_last_error(void) { return g_err; }
+
+__attribute__((visibility("default"))) uint64_t pws_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 __attribute__((visibility("default")))
 int pws_warp2d_forward(const pws_tensor *in, const pws_tensor *grid, pws_tensor *out,

@@ -179,11 +179,22 @@ template <typename T, int CS>
 void launch_cs(const Problem &pb, unsigned blocks, int tiles_x, int tiles_y, int n_begin, cudaStream_t st)
 {
     if (pb.want_gin && pb.want_ggrid)
-        bwd_march_kernel<T, CS, true, true><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, n_begin);
+        { bwd_march_kernel<T, CS, true, true><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, n_begin); note_launch(); }
     else if (pb.want_gin)
-        bwd_march_kernel<T, CS, true, false><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, n_begin);
+        { bwd_march_kernel<T, CS, true, false><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, n_begin); note_launch(); }
     else
-        bwd_march_kernel<T, CS, false, true><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, n_begin);
+        { bwd_march_kernel<T, CS, false, true><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, n_begin); note_launch(); }
+}
+
+}  // namespace
+bool backward_lean_eligible(const Problem &pb);                                  // warp_bwd_lean.cu
+void launch_backward_lean(const Problem &pb, int n0, int nn, cudaStream_t st);   // warp_bwd_lean.cu
+namespace {
+
+bool force_generic()
+{
+    static const bool v = [] { const char *e = std::getenv("PWS_FORCE_DIRECT"); return e && e[0] == '1'; }();
+    return v;
 }
 
 int64_t chunk_bytes()
@@ -191,7 +202,7 @@ int64_t chunk_bytes()
     // grad_input bytes zero-filled ahead of each scatter launch; must stay well inside L2
     static int64_t v = [] {
         const char *e = std::getenv("PWS_BWD_CHUNK_MB");
-        int64_t mb = e ? std::atoll(e) : 32;
+        int64_t mb = e ? std::atoll(e) : 64;
         if (mb < 1) mb = 1;
         return mb << 20;
     }();
@@ -210,6 +221,7 @@ int launch_typed(const Problem &pb, cudaStream_t st)
         if (per_chunk < 1) per_chunk = 1;
         if (per_chunk > g.N) per_chunk = g.N;
     }
+    const bool lean = sizeof(T) == 4 && !force_generic() && backward_lean_eligible(pb);
     const int cs = (g.C == 3) ? 3 : (g.C % 4 == 0) ? 4 : (g.C % 2 == 0) ? 2 : 1;
     for (int n0 = 0; n0 < g.N; n0 += per_chunk) {
         const int nn = (g.N - n0 < per_chunk) ? g.N - n0 : per_chunk;
@@ -218,6 +230,7 @@ int launch_typed(const Problem &pb, cudaStream_t st)
                                             (size_t)(frame_bytes * nn), st);
             if (e != cudaSuccess) { set_error("backward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return PWS_ECUDA; }
         }
+        if (lean) { launch_backward_lean(pb, n0, nn, st); continue; }
         const int64_t tiles = (int64_t)tiles_x * tiles_y * nn;
         if (tiles == 0) continue;
         if (tiles > INT_MAX) { set_error("backward: too many tiles"); return PWS_EUNSUPPORTED; }

@@ -11,6 +11,8 @@
 // any dependent gather (8 independent loads in flight per thread).
 #include "pws_common.cuh"
 
+#include <cstdlib>
+
 namespace pws {
 
 namespace {
@@ -110,16 +112,25 @@ int launch_direct(const Problem &pb, cudaStream_t st)
     const int64_t tiles = (int64_t)tiles_x * tiles_y * g.N;
     if (tiles > INT_MAX) { set_error("forward: too many tiles (%lld)", (long long)tiles); return PWS_EUNSUPPORTED; }
     dim3 grid_dim((unsigned)tiles), block(kThreads);
-    if (g.C == 3) fwd_direct_kernel<T, G, 3><<<grid_dim, block, 0, st>>>(pb.in, pb.grid, pb.out, g, tiles_x, tiles_y);
-    else if (g.C == 1) fwd_direct_kernel<T, G, 1><<<grid_dim, block, 0, st>>>(pb.in, pb.grid, pb.out, g, tiles_x, tiles_y);
-    else fwd_direct_kernel<T, G, 0><<<grid_dim, block, 0, st>>>(pb.in, pb.grid, pb.out, g, tiles_x, tiles_y);
+    if (g.C == 3) { fwd_direct_kernel<T, G, 3><<<grid_dim, block, 0, st>>>(pb.in, pb.grid, pb.out, g, tiles_x, tiles_y); note_launch(); }
+    else if (g.C == 1) { fwd_direct_kernel<T, G, 1><<<grid_dim, block, 0, st>>>(pb.in, pb.grid, pb.out, g, tiles_x, tiles_y); note_launch(); }
+    else { fwd_direct_kernel<T, G, 0><<<grid_dim, block, 0, st>>>(pb.in, pb.grid, pb.out, g, tiles_x, tiles_y); note_launch(); }
     return PWS_OK;
 }
 
 }  // namespace
 
+bool launch_forward_tile(const Problem &pb, cudaStream_t st);  // warp_fwd_tile.cu
+
+static bool force_direct()
+{
+    static const bool v = [] { const char *e = std::getenv("PWS_FORCE_DIRECT"); return e && e[0] == '1'; }();
+    return v;
+}
+
 int launch_forward(const Problem &pb, cudaStream_t st)
 {
+    if (!force_direct() && launch_forward_tile(pb, st)) return PWS_OK;
     const int it = pb.in_dtype, gt = pb.grid_dtype;
     if (it == PWS_F32 && gt == PWS_F32) return launch_direct<float, float>(pb, st);
     if (it == PWS_F64 && gt == PWS_F64) return launch_direct<double, double>(pb, st);
@@ -137,7 +148,7 @@ int launch_taps(const View &grid, const Geometry &g, int32_t *x0, int32_t *y0, u
     if (total == 0) return PWS_OK;
     const int64_t blocks = (total + 255) / 256;
     if (blocks > INT_MAX) { set_error("taps: too many pixels"); return PWS_EUNSUPPORTED; }
-    taps_kernel<<<(unsigned)blocks, 256, 0, st>>>(grid, g, x0, y0, mask, w, total);
+    { taps_kernel<<<(unsigned)blocks, 256, 0, st>>>(grid, g, x0, y0, mask, w, total); note_launch(); }
     return PWS_OK;
 }
 

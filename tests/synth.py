@@ -16,9 +16,12 @@ def identity_map(N, H, W, align_corners, dtype=np.float32):
     return g
 
 
-def smooth_drift(N, H, W, rng, amp=0.03, cells=8):
-    """amp * tanh(low-pass noise): mimics netG's +-0.035 drift."""
-    gh, gw = max(2, H // cells + 2), max(2, W // cells + 2)
+def smooth_drift(N, H, W, rng, amp=0.03, ncell=8):
+    """amp * tanh(low-pass noise): mimics netG's +-0.035 drift.  The noise
+    lives on an (ncell+1)^2 control lattice spanning the frame and is bilinearly
+    interpolated, so the local stretch is amp*ncell/2 of a pixel per pixel at most
+    (12 % for the defaults) whatever the resolution -- a stabilisation warp, not noise."""
+    gh = gw = ncell + 1
     coarse = rng.standard_normal((N, gh, gw, 2))
     ys = np.linspace(0, gh - 1.001, H)
     xs = np.linspace(0, gw - 1.001, W)
