@@ -29,8 +29,8 @@ template <int CS, bool kGin, bool kGgrid, bool kMasked>
 __device__ __forceinline__ void row_body(
     const int lane, const bool px_ok, const unsigned live,
     const float ix, const float iy, const float gxm, const float gym, const float (&go)[CS],
-    const float *__restrict__ ip, const int sH, const int64_t i_ch, const int H, const int W,
-    float *__restrict__ gip, const int64_t gi_ch,
+    const float *__restrict__ ip, const int sH, const int i_ch, const int H, const int W,
+    float *__restrict__ gip, const int gi_ch,
     float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy)
 {
     const float x0f = floorf(ix), y0f = floorf(iy);
@@ -49,7 +49,7 @@ __device__ __forceinline__ void row_body(
         float gix = 0.f, giy = 0.f;
 #pragma unroll
         for (int k = 0; k < CS; ++k) {
-            const float *__restrict__ pc = ip + k * i_ch + o_nw;
+            const float *__restrict__ pc = ip + (k * i_ch + o_nw);
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
             if (!kMasked || (mask & 1u)) v0 = __ldg(pc);
             if (!kMasked || (mask & 2u)) v1 = __ldg(pc + 1);
@@ -77,8 +77,7 @@ __device__ __forceinline__ void row_body(
             given = given && px_ok && ((live >> (lane + 1)) & 1u);
         }
         const bool chain = cy.live && cy.x == x0 && cy.y == y0;
-        float *__restrict__ p_nw = gip + o_nw;
-        float *__restrict__ p_cy = gip + (cy.y * sH + cy.x);
+        const int o_cy = cy.y * sH + cy.x;
 #pragma unroll
         for (int k = 0; k < CS; ++k) {
             float top = fmul(nw, go[k]), bot = fmul(sw, go[k]);
@@ -86,12 +85,12 @@ __device__ __forceinline__ void row_body(
             const float ptop = __shfl_up_sync(0xffffffffu, etop, 1), pbot = __shfl_up_sync(0xffffffffu, ebot, 1);
             if (take) { top += ptop; bot += pbot; }
             if (!given) {
-                if (mask & 2u) atomicAdd(p_nw + k * gi_ch + 1, etop);
-                if (mask & 8u) atomicAdd(p_nw + k * gi_ch + sH + 1, ebot);
+                if (mask & 2u) atomicAdd(gip + (k * gi_ch + o_nw + 1), etop);
+                if (mask & 8u) atomicAdd(gip + (k * gi_ch + o_nw + sH + 1), ebot);
             }
             if (chain) top += cy.v[k];
-            else if (cy.live) atomicAdd(p_cy + k * gi_ch, cy.v[k]);
-            if (mask & 1u) atomicAdd(p_nw + k * gi_ch, top);
+            else if (cy.live) atomicAdd(gip + (k * gi_ch + o_cy), cy.v[k]);
+            if (mask & 1u) atomicAdd(gip + (k * gi_ch + o_nw), top);
             cy.v[k] = bot;
         }
         cy.x = x0; cy.y = y0 + 1;
@@ -117,7 +116,7 @@ bwd_lean_kernel(const View gout, const View in, const View grid, const View gin,
     const float *__restrict__ ip = (const float *)in.p + (int64_t)n * in.sN;
     float *__restrict__ gip = kGin ? (float *)gin.p + (int64_t)n * gin.sN : nullptr;
     const int sH = in.s2;
-    const int64_t i_ch = in.s1, gi_ch = kGin ? (int64_t)gin.s1 : 0, go_ch = gout.s1;
+    const int i_ch = in.s1, gi_ch = kGin ? gin.s1 : 0, go_ch = gout.s1;  // 32-bit in-frame offsets (validated on the host)
 
     const bool inter = grid.s3 == 1;
     const float *__restrict__ gq = (const float *)grid.p + (int64_t)n * grid.sN + (int64_t)h0 * grid.s1 + (int64_t)w * grid.s2;
@@ -163,9 +162,9 @@ bwd_lean_kernel(const View gout, const View in, const View grid, const View gin,
         if (kGgrid) ggq += ggrid.s1;
     }
     if (kGin && cy.live) {
-        float *__restrict__ p_cy = gip + (cy.y * sH + cy.x);
+        const int o_cy = cy.y * sH + cy.x;
 #pragma unroll
-        for (int k = 0; k < CS; ++k) atomicAdd(p_cy + k * gi_ch, cy.v[k]);
+        for (int k = 0; k < CS; ++k) atomicAdd(gip + (k * gi_ch + o_cy), cy.v[k]);
     }
 }
 

@@ -120,7 +120,22 @@ int launch_direct(const Problem &pb, cudaStream_t st)
 
 }  // namespace
 
-bool launch_forward_tile(const Problem &pb, cudaStream_t st);  // warp_fwd_tile.cu
+bool launch_forward_tile(const Problem &pb, cudaStream_t st);              // warp_fwd_tile.cu (lean / staged)
+bool launch_forward_batch(const Problem &pb, int batch, cudaStream_t st);  // warp_fwd_batch.cu
+bool launch_forward_march(const Problem &pb, cudaStream_t st);             // warp_fwd_march.cu
+
+// PWS_FWD_MODE: b4 (default) | b2 = batched gather; lean | staged = warp_fwd_tile.cu variants
+static int batch_mode()
+{
+    static const int v = [] {
+        const char *e = std::getenv("PWS_FWD_MODE");
+        if (!e || !e[0]) return 4;
+        if (e[0] == 'b') return e[1] == '2' ? 2 : 4;
+        if (e[0] == 'm') return -1;  // marching kernel with register reuse
+        return 0;
+    }();
+    return v;
+}
 
 static bool force_direct()
 {
@@ -130,6 +145,8 @@ static bool force_direct()
 
 int launch_forward(const Problem &pb, cudaStream_t st)
 {
+    if (!force_direct() && batch_mode() < 0 && launch_forward_march(pb, st)) return PWS_OK;
+    if (!force_direct() && batch_mode() > 0 && launch_forward_batch(pb, batch_mode(), st)) return PWS_OK;
     if (!force_direct() && launch_forward_tile(pb, st)) return PWS_OK;
     const int it = pb.in_dtype, gt = pb.grid_dtype;
     if (it == PWS_F32 && gt == PWS_F32) return launch_direct<float, float>(pb, st);

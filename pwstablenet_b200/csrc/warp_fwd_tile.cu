@@ -82,7 +82,7 @@ fwd_tile_kernel(const View in, const View grid, const View out, const Geometry g
     }
 
     // ---- 3. gather
-    const int64_t o_row = (int64_t)kWarps * out.s2, o_ch = out.s1;
+    const int o_row = kWarps * out.s2, o_ch = out.s1;
     T *__restrict__ o0 = op + (int64_t)h_base * out.s2 + w_base;
     if (b.fits && b.all_valid && full) {
         // interior tile: no bounds checks, no tap masks
@@ -97,7 +97,7 @@ fwd_tile_kernel(const View in, const View grid, const View out, const Geometry g
                 const float wy1 = fsub(iy, y0f), wy0 = fsub(y0f + 1.0f, iy);
                 const float nw = fmul(wx0, wy0), ne = fmul(wx1, wy0), sw = fmul(wx0, wy1), se = fmul(wx1, wy1);
                 const T *__restrict__ sp = sb + (int)y0f * kBW + (int)x0f;
-                T *__restrict__ o = o0 + j * o_row + 32 * i;
+                T *__restrict__ o = o0 + (j * o_row + 32 * i);
 #pragma unroll
                 for (int c = 0; c < CS; ++c) {
                     const T *__restrict__ pc = sp + c * (kBH * kBW);
@@ -117,7 +117,7 @@ fwd_tile_kernel(const View in, const View grid, const View out, const Geometry g
             if (!(full || (w_base + 32 * i < g.Wo && h_base + kWarps * j < g.Ho))) continue;
             Taps<float> t;
             make_taps(sx[j][i], sy[j][i], g.H, g.W, t);
-            T *__restrict__ o = o0 + j * o_row + 32 * i;
+            T *__restrict__ o = o0 + (j * o_row + 32 * i);
             if (b.fits) {
                 const T *__restrict__ sp = s_box + (t.y0 - b.y0) * kBW + (t.x0 - b.x0);
 #pragma unroll
@@ -131,10 +131,10 @@ fwd_tile_kernel(const View in, const View grid, const View out, const Geometry g
                     o[c * o_ch] = from_acc<T, float>(acc);
                 }
             } else {
-                const T *__restrict__ p0 = ip + (int64_t)t.y0 * in.s2 + t.x0;
+                const T *__restrict__ p0 = ip + (t.y0 * in.s2 + t.x0);
 #pragma unroll
                 for (int c = 0; c < CS; ++c) {
-                    const T *__restrict__ pc = p0 + (int64_t)c * in.s1;
+                    const T *__restrict__ pc = p0 + c * in.s1;
                     float acc = 0.f;
                     if (t.mask & 1u) acc = ffma(to_acc(ldg(pc)), t.nw, acc);
                     if (t.mask & 2u) acc = ffma(to_acc(ldg(pc + 1)), t.ne, acc);
@@ -185,7 +185,7 @@ fwd_lean_kernel(const View in, const View grid, const View out, const Geometry g
                 }
             }
     }
-    const int64_t o_row = (int64_t)kWarps * out.s2, o_ch = out.s1, i_ch = in.s1;
+    const int o_row = kWarps * out.s2, o_ch = out.s1, i_ch = in.s1;  // 32-bit in-frame offsets
     const int sH = in.s2;
     T *__restrict__ o0 = op + (int64_t)h_base * out.s2 + w_base;
 #pragma unroll
@@ -197,7 +197,7 @@ fwd_lean_kernel(const View in, const View grid, const View out, const Geometry g
             const float iy = src_index<kBorder, kAlign>(sy[j][i], g.H, Hf, Hm1);
             const float x0f = floorf(ix), y0f = floorf(iy);
             const bool inside = x0f >= 0.0f && x0f <= Wm1 - 1.0f && y0f >= 0.0f && y0f <= Hm1 - 1.0f;
-            T *__restrict__ o = o0 + j * o_row + 32 * i;
+            T *__restrict__ o = o0 + (j * o_row + 32 * i);
             if (__all_sync(0xffffffffu, inside && ok)) {
                 const float wx1 = fsub(ix, x0f), wx0 = fsub(x0f + 1.0f, ix);
                 const float wy1 = fsub(iy, y0f), wy0 = fsub(y0f + 1.0f, iy);
@@ -217,7 +217,7 @@ fwd_lean_kernel(const View in, const View grid, const View out, const Geometry g
             } else if (ok) {
                 Taps<float> t;
                 make_taps(ix, iy, g.H, g.W, t);
-                const T *__restrict__ p0 = ip + (int64_t)t.y0 * sH + t.x0;
+                const T *__restrict__ p0 = ip + (t.y0 * sH + t.x0);
 #pragma unroll
                 for (int c = 0; c < CS; ++c) {
                     const T *__restrict__ pc = p0 + c * i_ch;

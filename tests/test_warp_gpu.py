@@ -299,3 +299,27 @@ def test_full_size_against_torch_cuda_and_conservation(pw, H, W, N):
     want = float((gout.double().sum(1) * valid_w).sum())
     got = float(fi.grad.double().sum())
     assert abs(got - want) <= 1e-6 * abs(want)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_frame_sharded_clip_equals_unsharded(pw, world):
+    # BASELINE config 4 in miniature: a clip cut into contiguous frame ranges, one per rank; the
+    # concatenation must be BIT-identical to the unsharded run (no reduction crosses ranks)
+    from pwstablenet_b200 import sharding
+    frames_n, C, H, W = 19, 3, 72, 128
+    frames = dev(synth.make_frames(frames_n, C, H, W, seed=21))
+    grid = dev(synth.make_map("smooth", frames_n, H, W, False, seed=22))
+    gout = dev(synth.make_gout(frames_n, C, H, W, seed=23))
+    full = pw.warp2d_forward(frames, grid, 0, False)
+    full_gin, full_gg = pw.warp2d_backward(gout, frames, grid, 0, False, (True, True))
+    outs, ggs = [], []
+    for r in range(world):
+        sh = sharding.shard_frames(frames_n, world, r)
+        if sh.count == 0:
+            continue
+        sl = slice(sh.begin, sh.end)
+        outs.append(pw.warp2d_forward(frames[sl], grid[sl], 0, False))
+        _, gg = pw.warp2d_backward(gout[sl], frames[sl], grid[sl], 0, False, (False, True))
+        ggs.append(gg)
+    assert torch.equal(torch.cat(outs), full)
+    assert torch.equal(torch.cat(ggs), full_gg)
