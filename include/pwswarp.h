@@ -107,6 +107,42 @@ int pws_warp2d_taps(const pws_tensor *grid, int64_t in_h, int64_t in_w,
                     int32_t *x0, int32_t *y0, uint8_t *mask, float *weights,
                     int padding, int align_corners, void *stream);
 
+/* ---- map composition fused into the sample -------------------
+ * The map is not read from memory but composed per output pixel:
+ *     lattice(i,j) = drift[n,i,j,:] + base(i,j)            on a (map_h x map_w) lattice
+ *     map(h,w)     = lattice(h,w)                           upsample == PWS_UP_NONE
+ *                  = bilinear resize of the lattice         PWS_UP_ALIGNED   (nn.UpsamplingBilinear2d,
+ *                    to the output size                                       R/main_new.py:706-710)
+ *                                                           PWS_UP_HALF_PIXEL (nn.Upsample(mode='bilinear'),
+ *                                                                             R/main.py:639-641)
+ * base: PWS_BASE_NONE      drift already is the map
+ *       PWS_BASE_IDENTITY  generate_maps' meshgrid X*2/(W-1)-1          (R/lib/utils.py:386-403)
+ *       PWS_BASE_AFFINE    F.affine_grid(theta, size, base_align_corners) (R/lib/networks_cascading.py:164,235)
+ * Around the sample: frame' = (frame + pre_add) * pre_mul, out = acc / post_div + post_add
+ * (R/main_new.py:106-107: (x+1)*127.5 ... /127.5-1); (0,1,1,0) switches them off.
+ * Frames may be PWS_U8 (cv2 HWC buffers, R/main_new.py:679-684) and the output PWS_U8
+ * (truncating store, R/main_new.py:717-721), PWS_F32, or the frame's 16-bit float type. */
+enum { PWS_BASE_NONE = 0, PWS_BASE_IDENTITY = 1, PWS_BASE_AFFINE = 2 };
+enum { PWS_UP_NONE = 0, PWS_UP_ALIGNED = 1, PWS_UP_HALF_PIXEL = 2 };
+
+typedef struct pws_map_spec {
+    const pws_tensor *drift; /* (N, map_h, map_w, 2) f32 view, any strides; NULL = zero drift */
+    const float *theta;      /* (N,2,3) f32 contiguous device memory; PWS_BASE_AFFINE only */
+    int32_t base;
+    int32_t base_align_corners;
+    int32_t upsample;
+    int32_t reserved;
+    int64_t map_h, map_w;
+    float pre_add, pre_mul, post_div, post_add;
+} pws_map_spec;
+
+/* Forward warp with the composed map; `out` (N,C,Ho,Wo) fixes the output size. */
+int pws_warp2d_forward_fused(const pws_tensor *in, const pws_map_spec *spec, pws_tensor *out,
+                             int padding, int align_corners, void *stream);
+
+/* Debug / parity: writes the map the fused kernel uses into map_out (N,Ho,Wo,2) f32. */
+int pws_compose_map(const pws_map_spec *spec, int64_t n, pws_tensor *map_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

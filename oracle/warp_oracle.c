@@ -368,7 +368,7 @@ static inline float affine_base_f32(int i, int S, int align)
 {
     if (S <= 1) return 0.0f;
     float step = 2.0f / (float)(S - 1);
-    float v = (i < S / 2) ? (-1.0f + step * (float)i) : (1.0f - step * (float)(S - 1 - i));
+    float v = (i < S / 2) ? fmaf(step, (float)i, -1.0f) : fmaf(-step, (float)(S - 1 - i), 1.0f); /* contracted, as on the GPU */
     if (!align) v = v * (float)(S - 1) / (float)S;
     return v;
 }

@@ -19,6 +19,8 @@ EXPORTS = (
     "pws_warp2d_forward",
     "pws_warp2d_backward",
     "pws_warp2d_taps",
+    "pws_warp2d_forward_fused",
+    "pws_compose_map",
 )
 
 
@@ -31,6 +33,26 @@ class PwsTensor(ctypes.Structure):
         ("stride", ctypes.c_int64 * 4),
     ]
 
+
+class PwsMapSpec(ctypes.Structure):
+    _fields_ = [
+        ("drift", ctypes.POINTER(PwsTensor)),
+        ("theta", ctypes.c_void_p),
+        ("base", ctypes.c_int32),
+        ("base_align_corners", ctypes.c_int32),
+        ("upsample", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("map_h", ctypes.c_int64),
+        ("map_w", ctypes.c_int64),
+        ("pre_add", ctypes.c_float),
+        ("pre_mul", ctypes.c_float),
+        ("post_div", ctypes.c_float),
+        ("post_add", ctypes.c_float),
+    ]
+
+
+PWS_BASE_NONE, PWS_BASE_IDENTITY, PWS_BASE_AFFINE = 0, 1, 2
+PWS_UP_NONE, PWS_UP_ALIGNED, PWS_UP_HALF_PIXEL = 0, 1, 2
 
 _lib = None
 
@@ -57,6 +79,11 @@ def load() -> ctypes.CDLL:
     lib.pws_warp2d_taps.restype = ctypes.c_int
     lib.pws_warp2d_taps.argtypes = [P, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    S = ctypes.POINTER(PwsMapSpec)
+    lib.pws_warp2d_forward_fused.restype = ctypes.c_int
+    lib.pws_warp2d_forward_fused.argtypes = [P, S, P, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.pws_compose_map.restype = ctypes.c_int
+    lib.pws_compose_map.argtypes = [S, ctypes.c_int64, P, ctypes.c_void_p]
     got = lib.pws_abi_version()
     if got != ABI_VERSION:
         raise RuntimeError(f"pwstablenet_b200: libpwswarp.so has ABI {got}, expected {ABI_VERSION}; rebuild it")

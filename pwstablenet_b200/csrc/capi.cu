@@ -156,6 +156,41 @@ int finish(const char *what)
 }  // namespace
 }  // namespace pws
 
+namespace pws {
+int launch_forward_fused(const View &in, int in_dtype, const MapSpec &m, const View &out, int out_dtype,
+                         const Geometry &g, cudaStream_t st);
+int launch_compose_map(const MapSpec &m, const View &out, int N, int Ho, int Wo, cudaStream_t st);
+
+static int make_spec(const pws_map_spec *spec, int64_t N, int64_t Ho, int64_t Wo, MapSpec *m)
+{
+    if (!spec) { set_error("map spec: null"); return PWS_EINVAL; }
+    if (spec->base < 0 || spec->base > 2 || spec->upsample < 0 || spec->upsample > 2) { set_error("map spec: bad base/upsample enum"); return PWS_EINVAL; }
+    if (spec->map_h <= 0 || spec->map_w <= 0 || spec->map_h > INT_MAX || spec->map_w > INT_MAX) { set_error("map spec: bad lattice size"); return PWS_EINVAL; }
+    m->drift.p = nullptr; m->drift.sN = 0; m->drift.s1 = m->drift.s2 = m->drift.s3 = 0;
+    if (spec->drift) {
+        if (spec->drift->dtype != PWS_F32) { set_error("map spec: drift must be f32"); return PWS_EUNSUPPORTED; }
+        if (spec->drift->size[0] != N || spec->drift->size[1] != spec->map_h || spec->drift->size[2] != spec->map_w || spec->drift->size[3] != 2) {
+            set_error("map spec: drift must have sizes [N, map_h, map_w, 2]"); return PWS_EINVAL;
+        }
+        int rc = make_view(spec->drift, "drift", &m->drift);
+        if (rc != PWS_OK) return rc;
+    } else if (spec->base == PWS_BASE_NONE) { set_error("map spec: no drift and no base"); return PWS_EINVAL; }
+    if (spec->base == PWS_BASE_AFFINE && !spec->theta) { set_error("map spec: affine base needs theta"); return PWS_EINVAL; }
+    if (spec->upsample == PWS_UP_NONE && (spec->map_h != Ho || spec->map_w != Wo)) {
+        set_error("map spec: lattice %lldx%lld differs from the output %lldx%lld and no upsample was requested",
+                  (long long)spec->map_h, (long long)spec->map_w, (long long)Ho, (long long)Wo);
+        return PWS_EINVAL;
+    }
+    m->theta = spec->theta; m->base = spec->base; m->base_align = spec->base_align_corners ? 1 : 0;
+    m->upsample = spec->upsample; m->mh = (int)spec->map_h; m->mw = (int)spec->map_w;
+    m->pre_add = spec->pre_add; m->pre_mul = spec->pre_mul; m->post_div = spec->post_div; m->post_add = spec->post_add;
+    m->has_pre = !(spec->pre_add == 0.0f && spec->pre_mul == 1.0f);
+    m->has_post = !(spec->post_div == 1.0f && spec->post_add == 0.0f);
+    if (spec->post_div == 0.0f) { set_error("map spec: post_div must not be 0"); return PWS_EINVAL; }
+    return PWS_OK;
+}
+}  // namespace pws
+
 using namespace pws;
 
 #define PWS_TRY(expr) do { int rc_ = (expr); if (rc_ != PWS_OK) return rc_; } while (0)
@@ -260,6 +295,46 @@ int pws_warp2d_taps(const pws_tensor *grid, int64_t in_h, int64_t in_w,
     if (!dg.ok) { set_error("taps: cannot select cuda:%d", grid->device); return PWS_ECUDA; }
     PWS_TRY(launch_taps(gv, g, x0, y0, mask, weights, (cudaStream_t)stream));
     return finish("taps");
+}
+
+__attribute__((visibility("default")))
+int pws_warp2d_forward_fused(const pws_tensor *in, const pws_map_spec *spec, pws_tensor *out,
+                             int padding, int align_corners, void *stream)
+{
+    PWS_TRY(check_modes(PWS_INTERP_BILINEAR, padding));
+    if (!in || !out) { set_error("fused forward: null tensor descriptor"); return PWS_EINVAL; }
+    for (int d = 2; d < 4; ++d)
+        if (in->size[d] <= 0) { set_error("grid_sampler(): expected input to have non-empty spatial dimensions"); return PWS_EINVAL; }
+    if (out->size[0] != in->size[0] || out->size[1] != in->size[1]) { set_error("fused forward: output batch/channels must equal the input's"); return PWS_EINVAL; }
+    if (out->device != in->device) { set_error("fused forward: output must be on the input's device"); return PWS_EINVAL; }
+    View vin, vout;
+    PWS_TRY(make_view(in, "input", &vin));
+    PWS_TRY(make_view(out, "output", &vout));
+    MapSpec m;
+    PWS_TRY(make_spec(spec, in->size[0], out->size[2], out->size[3], &m));
+    Geometry g{};
+    g.N = (int32_t)in->size[0]; g.C = (int32_t)in->size[1]; g.H = (int32_t)in->size[2]; g.W = (int32_t)in->size[3];
+    g.Ho = (int32_t)out->size[2]; g.Wo = (int32_t)out->size[3]; g.padding = padding; g.align = align_corners ? 1 : 0;
+    if ((int64_t)g.N * g.C * g.Ho * g.Wo == 0) return PWS_OK;
+    DeviceGuard dg(in->device);
+    if (!dg.ok) { set_error("fused forward: cannot select cuda:%d", in->device); return PWS_ECUDA; }
+    PWS_TRY(launch_forward_fused(vin, in->dtype, m, vout, out->dtype, g, (cudaStream_t)stream));
+    return finish("fused forward");
+}
+
+__attribute__((visibility("default")))
+int pws_compose_map(const pws_map_spec *spec, int64_t n, pws_tensor *map_out, void *stream)
+{
+    if (!map_out) { set_error("compose_map: null output"); return PWS_EINVAL; }
+    if (map_out->dtype != PWS_F32 || map_out->size[3] != 2 || map_out->size[0] != n) { set_error("compose_map: output must be f32 (N,Ho,Wo,2)"); return PWS_EINVAL; }
+    View vout;
+    PWS_TRY(make_view(map_out, "map_out", &vout));
+    MapSpec m;
+    PWS_TRY(make_spec(spec, n, map_out->size[1], map_out->size[2], &m));
+    DeviceGuard dg(map_out->device);
+    if (!dg.ok) { set_error("compose_map: cannot select cuda:%d", map_out->device); return PWS_ECUDA; }
+    PWS_TRY(launch_compose_map(m, vout, (int)n, (int)map_out->size[1], (int)map_out->size[2], (cudaStream_t)stream));
+    return finish("compose_map");
 }
 
 }  // extern "C"

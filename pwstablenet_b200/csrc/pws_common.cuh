@@ -140,6 +140,17 @@ struct Problem {  // validated, kernel-ready description of one call
     bool want_gin, want_ggrid;
 };
 
+struct MapSpec {  // kernel-side form of pws_map_spec (warp_fused.cu)
+    View drift;          // (N, mh, mw, 2) fp32; p == nullptr: zero drift
+    const float *theta;  // (N,2,3) for the affine base
+    int base;            // PWS_BASE_*
+    int base_align;      // align_corners of affine_grid
+    int upsample;        // PWS_UP_*
+    int mh, mw;          // map lattice size
+    float pre_add, pre_mul, post_div, post_add;
+    int has_pre, has_post;
+};
+
 int launch_forward(const Problem &pb, cudaStream_t st);
 int launch_backward(const Problem &pb, cudaStream_t st);
 int launch_taps(const View &grid, const Geometry &g, int32_t *x0, int32_t *y0, uint8_t *mask, float *w, cudaStream_t st);
