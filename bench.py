@@ -10,7 +10,7 @@ FRAMES 1080p fp32 RGB frames per GPU, through the C ABI of libpwswarp.so.
   value        frames/s, whole job, inputs resident in HBM (inputs are 0.9 GB per GPU,
                larger than the 126 MB L2, so every step streams from DRAM)
   e2e          same metric through the user-facing call (pwstablenet_b200.grid_sample
-               + .backward) with PINNED HOST buffers: H2D of frames/map/grad_output and
+               pipeline) with PINNED HOST buffers: H2D of frames/map/grad_output and
                D2H of output/grad_frame/grad_map inside the timed region
   roofline     backward kernel (the dominant one): algorithmic bytes (52 B/pixel)
                / CUDA-event time of the backward call, against MEASURED_PEAKS.json
@@ -259,15 +259,11 @@ def main():
     h2d = hf.numel() * 4 + hg.numel() * 4 + hgo.numel() * 4
     d2h = h_out.numel() * 4 + h_gin.numel() * 4 + h_gg.numel() * 4
 
+    # the user-facing host API: chunks of 2 frames, upload / warp / download overlapped on three streams
+    pipe = pw.HostWarpPipeline(2, C, (H, W), device=dev, backward=True)
+
     def step_e2e():
-        f = hf.to(dev, non_blocking=True).requires_grad_(True)
-        g = hg.to(dev, non_blocking=True).permute(0, 2, 3, 1).requires_grad_(True)   # planar-stored view
-        go = hgo.to(dev, non_blocking=True)
-        o = pw.grid_sample(f, g, mode="bilinear", padding_mode="zeros", align_corners=False)
-        o.backward(go)
-        h_out.copy_(o.detach(), non_blocking=True)
-        h_gin.copy_(f.grad, non_blocking=True)
-        h_gg.copy_(g.grad.permute(0, 3, 1, 2), non_blocking=True)
+        pipe.run(hf, hg, h_out, hgo, h_gin, h_gg)
 
     e2e_steps = max(3, min(steps, 10))
     for _ in range(2):
@@ -306,7 +302,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * FRAMES * e2e_steps / (e2e_ms * 1e-3), "unit": "frames/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "pwstablenet_b200.grid_sample(...).backward() on tensors copied from pinned host memory"},
+                    "api": "pwstablenet_b200.HostWarpPipeline.run(): pinned host buffers in and out, 2-frame chunks, H2D / fwd+bwd through the C ABI / D2H overlapped on 3 streams"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "bwd_lean_kernel (pws_warp2d_backward)", "achieved": bwd_gbs, "peak": peak,
                          "unit": "GB/s", "frac": bwd_gbs / peak, "peak_source": peak_src, "traffic": None,

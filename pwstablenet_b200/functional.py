@@ -73,11 +73,14 @@ def _require_cuda(input: torch.Tensor, grid: torch.Tensor) -> None:
         )
 
 
-def warp2d_forward(input: torch.Tensor, grid: torch.Tensor, padding: int, align_corners: bool) -> torch.Tensor:
-    """aten::grid_sampler_2d replacement (bilinear). Returns an NCHW-contiguous tensor, as ATen does."""
+def warp2d_forward(input: torch.Tensor, grid: torch.Tensor, padding: int, align_corners: bool,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """aten::grid_sampler_2d replacement (bilinear). Returns an NCHW-contiguous tensor, as ATen does
+    (or fills the caller's `out`)."""
     lib = _lib.load()
     N, C = input.size(0), input.size(1)
-    out = torch.empty((N, C, grid.size(1), grid.size(2)), dtype=input.dtype, device=input.device)
+    if out is None:
+        out = torch.empty((N, C, grid.size(1), grid.size(2)), dtype=input.dtype, device=input.device)
     with torch.cuda.device_of(input):
         rc = lib.pws_warp2d_forward(ctypes.byref(_desc(input)), ctypes.byref(_desc(grid)), ctypes.byref(_desc(out)),
                                     0, padding, int(align_corners), _stream(input))
@@ -99,13 +102,18 @@ def _like_layout(t: torch.Tensor) -> torch.Tensor:
 
 
 def warp2d_backward(grad_output: torch.Tensor, input: torch.Tensor, grid: torch.Tensor, padding: int,
-                    align_corners: bool, output_mask=(True, True)):
-    """aten::grid_sampler_2d_backward replacement. Returns (grad_input | None, grad_grid | None)."""
+                    align_corners: bool, output_mask=(True, True), grad_input: Optional[torch.Tensor] = None,
+                    grad_grid: Optional[torch.Tensor] = None):
+    """aten::grid_sampler_2d_backward replacement. Returns (grad_input | None, grad_grid | None);
+    caller-provided buffers are filled when given (grad_input need not be zeroed)."""
     lib = _lib.load()
     if grid.dtype != input.dtype:
         raise NotImplementedError("pwstablenet_b200: backward needs the map in the frame's dtype")
-    gin = torch.empty(input.size(), dtype=input.dtype, device=input.device) if output_mask[0] else None
-    ggrid = _like_layout(grid) if output_mask[1] else None
+    gin = ggrid = None
+    if output_mask[0]:
+        gin = grad_input if grad_input is not None else torch.empty(input.size(), dtype=input.dtype, device=input.device)
+    if output_mask[1]:
+        ggrid = grad_grid if grad_grid is not None else _like_layout(grid)
     with torch.cuda.device_of(input):
         rc = lib.pws_warp2d_backward(
             ctypes.byref(_desc(grad_output)), ctypes.byref(_desc(input)), ctypes.byref(_desc(grid)),

@@ -323,3 +323,21 @@ def test_frame_sharded_clip_equals_unsharded(pw, world):
         ggs.append(gg)
     assert torch.equal(torch.cat(outs), full)
     assert torch.equal(torch.cat(ggs), full_gg)
+
+
+def test_host_pipeline_matches_device_path(pw):
+    # HostWarpPipeline is plumbing: results must equal the device-resident calls (forward and
+    # grad_grid bit for bit; grad_input within the atomic-order tolerance)
+    n, C, H, W = 7, 3, 120, 200
+    frames = torch.from_numpy(synth.make_frames(n, C, H, W, seed=31)).pin_memory()
+    maps = torch.from_numpy(np.ascontiguousarray(synth.make_map("smooth", n, H, W, False, seed=32).transpose(0, 3, 1, 2))).pin_memory()
+    gout = torch.from_numpy(synth.make_gout(n, C, H, W, seed=33)).pin_memory()
+    out, gf, gm = pw.warp_host(frames, maps, gout, chunk=2)
+    grid = maps.cuda().permute(0, 2, 3, 1)
+    want = pw.warp2d_forward(frames.cuda(), grid, 0, False)
+    w_gin, w_gg = pw.warp2d_backward(gout.cuda(), frames.cuda(), grid, 0, False, (True, True))
+    assert torch.equal(out, want.cpu())
+    assert torch.equal(gm, w_gg.permute(0, 3, 1, 2).contiguous().cpu())
+    assert float((gf - w_gin.cpu()).abs().max()) <= 1e-4 * float(w_gin.abs().max())
+    out2, gf2, gm2 = pw.warp_host(frames, maps, None, chunk=3)
+    assert gf2 is None and torch.equal(out2, out)
