@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-cudart", "shared",
-]
+] + os.environ.get("PWS_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpwswarp.so")
+LIB_PATH = os.environ.get("PWS_LIB_PATH") or os.path.join(HERE, "libpwswarp.so")  # override: A/B of kernel builds
 
 PWS_F32, PWS_F16, PWS_BF16, PWS_F64, PWS_U8, PWS_I32 = range(6)
 PWS_OK, PWS_EINVAL, PWS_EUNSUPPORTED, PWS_ECUDA = 0, -1, -2, -3

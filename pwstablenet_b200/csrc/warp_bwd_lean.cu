@@ -31,7 +31,7 @@ __device__ __forceinline__ void row_body(
     const float ix, const float iy, const float gxm, const float gym, const float (&go)[CS],
     const float *__restrict__ ip, const int sH, const int i_ch, const int H, const int W,
     float *__restrict__ gip, const int gi_ch,
-    float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy)
+    float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy, int2 *__restrict__ queue)
 {
     const float x0f = floorf(ix), y0f = floorf(iy);
     const int x0 = (int)x0f, y0 = (int)y0f;
@@ -78,20 +78,38 @@ __device__ __forceinline__ void row_body(
         }
         const bool chain = cy.live && cy.x == x0 && cy.y == y0;
         const int o_cy = cy.y * sH + cy.x;
+        // Left-overs -- east taps nobody takes over, parked south sums whose chain broke -- exist on a
+        // few lanes of almost every row of a stretched map.  The L2 accepts ~25 G RED instructions/s
+        // whether 1 or 32 lanes are active (tools/exp/exp_red.cu), and issuing them per class made the
+        // scatter run exactly at that ceiling (9 of 12 REDs per row).  They are compacted through a
+        // small per-warp queue in shared memory instead and leave as one dense RED.
+        const bool p_e1 = !given && (mask & 2u), p_e2 = !given && (mask & 8u), p_f = cy.live && !chain;
+        const unsigned b_e1 = __ballot_sync(0xffffffffu, p_e1), b_e2 = __ballot_sync(0xffffffffu, p_e2);
+        const unsigned b_f = __ballot_sync(0xffffffffu, p_f);
+        const unsigned lt = (1u << lane) - 1u;
+        const int n_e1 = __popc(b_e1), n_e2 = __popc(b_e2), n_f = __popc(b_f);
+        const int s_e1 = __popc(b_e1 & lt), s_e2 = CS * n_e1 + __popc(b_e2 & lt), s_f = CS * (n_e1 + n_e2) + __popc(b_f & lt);
 #pragma unroll
         for (int k = 0; k < CS; ++k) {
             float top = fmul(nw, go[k]), bot = fmul(sw, go[k]);
             const float etop = fmul(ne, go[k]), ebot = fmul(se, go[k]);
             const float ptop = __shfl_up_sync(0xffffffffu, etop, 1), pbot = __shfl_up_sync(0xffffffffu, ebot, 1);
             if (take) { top += ptop; bot += pbot; }
-            if (!given) {
-                if (mask & 2u) atomicAdd(gip + (k * gi_ch + o_nw + 1), etop);
-                if (mask & 8u) atomicAdd(gip + (k * gi_ch + o_nw + sH + 1), ebot);
-            }
+            if (p_e1) queue[s_e1 + k * n_e1] = make_int2(k * gi_ch + o_nw + 1, __float_as_int(etop));
+            if (p_e2) queue[s_e2 + k * n_e2] = make_int2(k * gi_ch + o_nw + sH + 1, __float_as_int(ebot));
             if (chain) top += cy.v[k];
-            else if (cy.live) atomicAdd(gip + (k * gi_ch + o_cy), cy.v[k]);
+            if (p_f) queue[s_f + k * n_f] = make_int2(k * gi_ch + o_cy, __float_as_int(cy.v[k]));
             if (mask & 1u) atomicAdd(gip + (k * gi_ch + o_nw), top);
             cy.v[k] = bot;
+        }
+        const int n_items = CS * (n_e1 + n_e2 + n_f);
+        if (n_items > 0) {
+            __syncwarp();
+            for (int i = lane; i < n_items; i += 32) {
+                const int2 it = queue[i];
+                atomicAdd(gip + it.x, __int_as_float(it.y));
+            }
+            __syncwarp();
         }
         cy.x = x0; cy.y = y0 + 1;
         cy.live = (mask & 4u) != 0u;
@@ -99,11 +117,16 @@ __device__ __forceinline__ void row_body(
 }
 
 template <int CS, bool kBorder, bool kAlign, bool kGin, bool kGgrid>
-__global__ void __launch_bounds__(kThreads, 3)
+#ifndef PWS_BWD_MINB
+#define PWS_BWD_MINB 4   // 64 registers, 32 warps/SM: measured 5-9 % faster than 3 CTAs at 80 registers
+#endif
+__global__ void __launch_bounds__(kThreads, PWS_BWD_MINB)
 bwd_lean_kernel(const View gout, const View in, const View grid, const View gin, const View ggrid,
                 const Geometry g, const int n_begin)
 {
+    __shared__ int2 s_queue[kGin ? kThreads / 32 : 1][kGin ? 3 * CS * 32 : 1];  // per warp: every lane, 3 classes, CS channels
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    int2 *const queue = s_queue[kGin ? wrp : 0];
     const int n = n_begin + blockIdx.z;
     const int w = blockIdx.x * kTW + (wrp % kWarpsX) * 32 + lane;
     const int h0 = blockIdx.y * kTH + (wrp / kWarpsX) * kRows;
@@ -156,9 +179,9 @@ bwd_lean_kernel(const View gout, const View in, const View grid, const View gin,
         const float iy = src_index_grad<kBorder, kAlign>(gy, Hf, Hm1, &gym);
         const bool inside = col_ok && ix >= 0.0f && ix < Wm1 && iy >= 0.0f && iy < Hm1;  // floor in [0, size-2]
         if (__all_sync(0xffffffffu, inside))
-            row_body<CS, kGin, kGgrid, false>(lane, true, live, ix, iy, gxm, gym, go, ip, sH, i_ch, g.H, g.W, gip, gi_ch, ggq, ggrid.s3, cy);
+            row_body<CS, kGin, kGgrid, false>(lane, true, live, ix, iy, gxm, gym, go, ip, sH, i_ch, g.H, g.W, gip, gi_ch, ggq, ggrid.s3, cy, queue);
         else
-            row_body<CS, kGin, kGgrid, true>(lane, col_ok, live, ix, iy, gxm, gym, go, ip, sH, i_ch, g.H, g.W, gip, gi_ch, ggq, ggrid.s3, cy);
+            row_body<CS, kGin, kGgrid, true>(lane, col_ok, live, ix, iy, gxm, gym, go, ip, sH, i_ch, g.H, g.W, gip, gi_ch, ggq, ggrid.s3, cy, queue);
         if (kGgrid) ggq += ggrid.s1;
     }
     if (kGin && cy.live) {

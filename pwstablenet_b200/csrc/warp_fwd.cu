@@ -124,12 +124,12 @@ bool launch_forward_tile(const Problem &pb, cudaStream_t st);              // wa
 bool launch_forward_batch(const Problem &pb, int batch, cudaStream_t st);  // warp_fwd_batch.cu
 bool launch_forward_march(const Problem &pb, cudaStream_t st);             // warp_fwd_march.cu
 
-// PWS_FWD_MODE: b4 (default) | b2 = batched gather; lean | staged = warp_fwd_tile.cu variants
+// PWS_FWD_MODE: lean (default) | staged = warp_fwd_tile.cu; b2 | b4 = batched gather; m = marching (experiments)
 static int batch_mode()
 {
     static const int v = [] {
         const char *e = std::getenv("PWS_FWD_MODE");
-        if (!e || !e[0]) return 4;
+        if (!e || !e[0]) return 0;   // default: lean kernel (warp_fwd_tile.cu), the fastest measured
         if (e[0] == 'b') return e[1] == '2' ? 2 : 4;
         if (e[0] == 'm') return -1;  // marching kernel with register reuse
         return 0;

@@ -29,7 +29,7 @@ template <int MODE>
 int run(const char *name, float *p, size_t n_floats, int reps, bool prezero)
 {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    const int blocks = 148 * 8, threads = 256;
+    const int blocks = 148 * 8, threads = 512;
     for (int it = 0; it < 3; ++it) {
         if (prezero) CK(cudaMemsetAsync(p, 0, n_floats * 4));
         cudaEventRecord(a);
@@ -53,7 +53,7 @@ int main()
     const size_t big = (size_t)256 << 20;  // 1 GiB of floats
     CK(cudaMalloc(&p, big * 4));
     for (size_t n : {(size_t)6 << 20, (size_t)256 << 20}) {   // 24 MB (L2 resident) and 1 GB
-        const int reps = 64;
+        const int reps = 512;
         run<0>("RED.32 full warp, aligned", p, n, reps, true);
         run<1>("RED.32 full warp, +1 float", p, n, reps, true);
         run<2>("RED.128 (v4) full warp", p, n, reps, true);
