@@ -1,0 +1,162 @@
+// pws_pipe.cuh -- pieces shared by the TMA-pipelined persistent kernels (warp_fwd_tma.cu, warp_bwd_tma.cu).
+//
+// Tile geometry, the shapes of the frame box a tile may request, and the "scout": the warp that turns
+// a map tile (already in shared memory) into the bounding box of the source taps it implies and picks
+// the smallest box shape that holds it.  The box IS the tile's halo under the map (north_star: "TMA
+// staging of the source-tile halo implied by each output tile's warp-map bounding box").
+#pragma once
+#include "pws_tile.cuh"
+#include "pws_tma.cuh"
+
+namespace pws {
+namespace pipe {
+
+constexpr int kTW = 64, kTH = 16;                      // output pixels per tile
+constexpr int kMapTileFloats = 2 * kTW * kTH;
+constexpr int kMapTileBytes = kMapTileFloats * 4;
+constexpr int kNumShapes = 3;
+constexpr int kBW0 = 72, kBH0 = 20, kBW1 = 80, kBH1 = 24, kBW2 = 88, kBH2 = 28;  // box shapes, smallest first
+constexpr int kMaxBW = kBW2, kMaxBH = kBH2;
+__host__ __device__ constexpr int box_w(int s) { return s == 0 ? kBW0 : s == 1 ? kBW1 : kBW2; }
+__host__ __device__ constexpr int box_h(int s) { return s == 0 ? kBH0 : s == 1 ? kBH1 : kBH2; }
+
+// info.z of a tile: box shape in the low byte plus
+enum : int {
+    kInfoInterior = 1 << 8,   // every tap of every pixel is inside the frame and the tile is full: mask-free body
+    kInfoFallback = 1 << 9,   // no box was loaded (does not fit / NaN / inf in the map): gather from global memory
+    kInfoEmpty = 1 << 10      // no tap of the tile is inside the frame: nothing was loaded, nothing is read
+};
+
+__device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fmin3_nan(float a, float b, float c) { float r; asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) { float r; asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float fmin4(const float4 v) { return fmin_nan(fmin3_nan(v.x, v.y, v.z), v.w); }
+__device__ __forceinline__ float fmax4(const float4 v) { return fmax_nan(fmax3_nan(v.x, v.y, v.z), v.w); }
+
+// raw unnormalised coordinate (no clip, no guard): monotone in `coord`
+template <bool kAlign>
+__device__ __forceinline__ float unnorm(float coord, float size_f, float size_m1_f)
+{
+    const float t = __fadd_rn(coord, 1.0f);
+    return kAlign ? __fmul_rn(__fmul_rn(t, 0.5f), size_m1_f) : __fmul_rn(__fmaf_rn(t, size_f, -1.0f), 0.5f);
+}
+
+// floor for 0 <= v < 2^22 without the conversion pipe: one round-down add against 1.5 * 2^23
+__device__ __forceinline__ void floor_small(float v, float &vf, int &vi)
+{
+    const float t = __fadd_rd(v, 12582912.0f);
+    vf = __fsub_rn(t, 12582912.0f);
+    vi = __float_as_int(t) - 0x4B400000;
+}
+
+struct TileCoord { int n, h0, w0; };
+__device__ __forceinline__ TileCoord tile_coord(int t, int tiles_x, int tiles_xy)
+{
+    TileCoord c;
+    c.n = t / tiles_xy;
+    const int r = t - c.n * tiles_xy;
+    const int ty = r / tiles_x;
+    c.h0 = ty * kTH;
+    c.w0 = (r - ty * tiles_x) * kTW;
+    return c;
+}
+
+// Extremes of the x and y map values of a tile, over its valid rows x cols, NaN-propagating.
+// Planar tile: [2][kTH][kTW]; interleaved: [kTH][kTW][2].  All 32 lanes of a warp call this.
+template <bool kInter>
+__device__ __forceinline__ void map_tile_range(const float *__restrict__ mp, int rows, int cols, int lane,
+                                               float &xlo, float &xhi, float &ylo, float &yhi)
+{
+    xlo = INFINITY; xhi = -INFINITY; ylo = INFINITY; yhi = -INFINITY;
+    if (rows == kTH && cols == kTW) {
+        // full tile: 16 independent 128-bit reads per lane, then a tree
+        float4 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = *reinterpret_cast<const float4 *>(mp + (k * 32 + lane) * 4);
+        if (kInter) {
+            // (x0,y0,x1,y1) quads: four independent chains per extreme
+            float a[4], b[4], c[4], d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { a[k] = INFINITY; b[k] = -INFINITY; c[k] = INFINITY; d[k] = -INFINITY; }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                a[k & 3] = fmin3_nan(a[k & 3], v[k].x, v[k].z); b[k & 3] = fmax3_nan(b[k & 3], v[k].x, v[k].z);
+                c[k & 3] = fmin3_nan(c[k & 3], v[k].y, v[k].w); d[k & 3] = fmax3_nan(d[k & 3], v[k].y, v[k].w);
+            }
+            xlo = fmin_nan(fmin_nan(a[0], a[1]), fmin_nan(a[2], a[3])); xhi = fmax_nan(fmax_nan(b[0], b[1]), fmax_nan(b[2], b[3]));
+            ylo = fmin_nan(fmin_nan(c[0], c[1]), fmin_nan(c[2], c[3])); yhi = fmax_nan(fmax_nan(d[0], d[1]), fmax_nan(d[2], d[3]));
+        } else {
+            // v[0..7] lie in the x plane, v[8..15] in the y plane
+            float lo[16], hi[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { lo[k] = fmin4(v[k]); hi[k] = fmax4(v[k]); }
+            xlo = fmin_nan(fmin3_nan(lo[0], lo[1], lo[2]), fmin_nan(fmin3_nan(lo[3], lo[4], lo[5]), fmin_nan(lo[6], lo[7])));
+            xhi = fmax_nan(fmax3_nan(hi[0], hi[1], hi[2]), fmax_nan(fmax3_nan(hi[3], hi[4], hi[5]), fmax_nan(hi[6], hi[7])));
+            ylo = fmin_nan(fmin3_nan(lo[8], lo[9], lo[10]), fmin_nan(fmin3_nan(lo[11], lo[12], lo[13]), fmin_nan(lo[14], lo[15])));
+            yhi = fmax_nan(fmax3_nan(hi[8], hi[9], hi[10]), fmax_nan(fmax3_nan(hi[11], hi[12], hi[13]), fmax_nan(hi[14], hi[15])));
+        }
+    } else if (kInter) {
+        const int c2 = lane * 2;  // rows of 64 (x,y) pairs: a lane covers 2 pairs of every row
+        if (c2 < cols)
+            for (int r = 0; r < rows; ++r) {
+                const float4 v = *reinterpret_cast<const float4 *>(mp + r * (2 * kTW) + 2 * c2);
+                xlo = fmin3_nan(xlo, v.x, v.z); xhi = fmax3_nan(xhi, v.x, v.z);
+                ylo = fmin3_nan(ylo, v.y, v.w); yhi = fmax3_nan(yhi, v.y, v.w);
+            }
+    } else {
+        const int c4 = (lane & 15) * 4;
+        if (c4 < cols)
+            for (int r = lane >> 4; r < rows; r += 2) {
+                const float4 vx = *reinterpret_cast<const float4 *>(mp + r * kTW + c4);
+                const float4 vy = *reinterpret_cast<const float4 *>(mp + kTW * kTH + r * kTW + c4);
+                xlo = fmin_nan(xlo, fmin4(vx)); xhi = fmax_nan(xhi, fmax4(vx));
+                ylo = fmin_nan(ylo, fmin4(vy)); yhi = fmax_nan(yhi, fmax4(vy));
+            }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        xlo = fmin_nan(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+        xhi = fmax_nan(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+        ylo = fmin_nan(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
+        yhi = fmax_nan(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+    }
+}
+
+// From the extremes of a tile's map to the box of the frame its taps need: (bx, by, shape | flags).
+// unnormalise is monotone, so the extremes of the map give the extremes of the taps.
+template <bool kBorder, bool kAlign>
+__device__ __forceinline__ int4 box_of_range(float xlo, float xhi, float ylo, float yhi, int W, int H, bool full_tile)
+{
+    const float Wf = (float)W, Hf = (float)H, Wm1 = (float)(W - 1), Hm1 = (float)(H - 1);
+    const float fxlo = unnorm<kAlign>(xlo, Wf, Wm1), fxhi = unnorm<kAlign>(xhi, Wf, Wm1);
+    const float fylo = unnorm<kAlign>(ylo, Hf, Hm1), fyhi = unnorm<kAlign>(yhi, Hf, Hm1);
+    // NaN / inf / beyond +-2^30: ATen's -100 guard breaks the monotonicity -> generic path
+    const bool sane = fxlo >= -1073741824.0f && fxhi <= 1073741824.0f && fylo >= -1073741824.0f && fyhi <= 1073741824.0f;
+    if (!sane) return make_int4(0, 0, kInfoFallback, 0);
+    int x0lo = __float2int_rd(fxlo), x0hi = __float2int_rd(fxhi);
+    int y0lo = __float2int_rd(fylo), y0hi = __float2int_rd(fyhi);
+    const bool interior = x0lo >= 0 && x0hi + 1 <= W - 1 && y0lo >= 0 && y0hi + 1 <= H - 1 && full_tile;
+    if (kBorder) {  // border padding clips the coordinate into [0, size-1] before the floor
+        x0lo = clampi(x0lo, 0, W - 1); x0hi = clampi(x0hi, 0, W - 1);
+        y0lo = clampi(y0lo, 0, H - 1); y0hi = clampi(y0hi, 0, H - 1);
+    }
+    // taps outside the frame are never read: clamp the box to the frame.
+    // TMA wants the box start 16-byte aligned: x rounds down to a multiple of 4 elements.
+    const int bx = max(x0lo, 0) & ~3, by = max(y0lo, 0);
+    const int bw = min(x0hi + 1, W - 1) - bx + 1, bh = min(y0hi + 1, H - 1) - by + 1;
+    if (bw <= 0 || bh <= 0) return make_int4(0, 0, kInfoEmpty, 0);
+    const int shape = bw <= kBW0 && bh <= kBH0 ? 0 : bw <= kBW1 && bh <= kBH1 ? 1 : bw <= kBW2 && bh <= kBH2 ? 2 : -1;
+    if (shape < 0) return make_int4(0, 0, kInfoFallback, 0);
+    return make_int4(bx, by, shape | (interior ? kInfoInterior : 0), 0);
+}
+
+}  // namespace pipe
+
+// host side (warp_fwd_tma.cu)
+bool encode_map_tma(const View &grid, const Geometry &g, CUtensorMap *tm, bool *inter);
+bool encode_frame_tma(const View &v, int W, int H, int C, int N, int bw, int bh, int bc, CUtensorMap *tm);
+bool tma_disabled();
+int sm_count();
+
+}  // namespace pws

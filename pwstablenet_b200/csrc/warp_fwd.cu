@@ -120,6 +120,7 @@ int launch_direct(const Problem &pb, cudaStream_t st)
 
 }  // namespace
 
+bool launch_forward_tma(const Problem &pb, cudaStream_t st);               // warp_fwd_tma.cu (TMA-pipelined persistent)
 bool launch_forward_tile(const Problem &pb, cudaStream_t st);              // warp_fwd_tile.cu (lean / staged)
 bool launch_forward_batch(const Problem &pb, int batch, cudaStream_t st);  // warp_fwd_batch.cu
 bool launch_forward_march(const Problem &pb, cudaStream_t st);             // warp_fwd_march.cu
@@ -147,6 +148,7 @@ int launch_forward(const Problem &pb, cudaStream_t st)
 {
     if (!force_direct() && batch_mode() < 0 && launch_forward_march(pb, st)) return PWS_OK;
     if (!force_direct() && batch_mode() > 0 && launch_forward_batch(pb, batch_mode(), st)) return PWS_OK;
+    if (!force_direct() && launch_forward_tma(pb, st)) return PWS_OK;
     if (!force_direct() && launch_forward_tile(pb, st)) return PWS_OK;
     const int it = pb.in_dtype, gt = pb.grid_dtype;
     if (it == PWS_F32 && gt == PWS_F32) return launch_direct<float, float>(pb, st);

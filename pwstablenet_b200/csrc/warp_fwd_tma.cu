@@ -1,0 +1,324 @@
+// warp_fwd_tma.cu -- TMA-pipelined persistent forward warp (sm_100a).
+//
+// Call sites: R/main_new.py:106,116 (NCHW fp32 frames, planar-stored maps), :197 (interleaved
+// affine_grid maps), :716 (the same at native video resolution).
+//
+// One persistent CTA per SM walks 64x16 tiles of OUTPUT pixels.  Three roles, mbarrier rings between them:
+//   warp 0  producer  streams the tile's warp map into shared memory (TMA, kMapStages ahead);
+//   warps 1-2 scouts  (alternate tiles) reduce the map tile to the bounding box of the source taps it implies --
+//                     the tile's halo under the map -- picks the smallest of three box shapes that
+//                     holds it and issues the TMA load of that box of the frame (all channels);
+//   warps 3-10 consumers gather the four taps of every pixel out of the shared-memory box and
+//                     store the result with 128-byte coalesced writes.
+// Neither the map nor the frame is touched by a generic load, so no warp ever waits on DRAM with
+// its own registers: HBM latency is covered by the depth of the two rings instead of by occupancy.
+// Tiles whose every tap is inside the frame run a mask-free body; tiles whose box fits no shape
+// (violent maps) or whose map holds NaN/inf gather from global memory inside the same kernel.
+// Arithmetic is the ATen order of pws_common.cuh / pws_tile.cuh: results are bit-identical to the
+// other forward kernels.
+#include "pws_pipe.cuh"
+
+#include <cstdlib>
+
+namespace pws {
+
+using namespace pipe;
+
+namespace {
+
+constexpr int kScouts = 2, kConsumers = 8, kThreads = (1 + kScouts + kConsumers) * 32;
+constexpr int kMapStages = 6, kBoxStages = 5;
+
+template <int CS> struct Smem {
+    static constexpr int kBoxBytes = kMaxBW * kMaxBH * CS * 4;
+    static constexpr int kMapOff = 0;
+    static constexpr int kBoxOff = kMapStages * kMapTileBytes;
+    static constexpr int kInfoOff = kBoxOff + kBoxStages * kBoxBytes;
+    static constexpr int kBarOff = kInfoOff + kBoxStages * 16;
+    static constexpr int kTotal = kBarOff + (2 * kMapStages + 2 * kBoxStages) * 8;
+    static_assert(kBoxBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
+};
+
+struct TmaParams {
+    CUtensorMap map;                // planar: (Wo, Ho, 2, N) box (64,16,2,1); interleaved: (2Wo, Ho, N) box (128,16,1)
+    CUtensorMap box[kNumShapes];    // frame (W, H, C, N), box (BW, BH, CS, 1)
+};
+
+template <int CS, bool kBorder, bool kAlign, bool kInter>
+__global__ void __launch_bounds__(kThreads, 1)
+fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View out, const Geometry g,
+               const int tiles_x, const int tiles_y, const int total_tiles)
+{
+    using S = Smem<CS>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float *const s_map = reinterpret_cast<float *>(smem + S::kMapOff);
+    unsigned char *const s_box = smem + S::kBoxOff;
+    int4 *const s_info = reinterpret_cast<int4 *>(smem + S::kInfoOff);
+    uint64_t *const map_full = reinterpret_cast<uint64_t *>(smem + S::kBarOff);
+    uint64_t *const map_empty = map_full + kMapStages;
+    uint64_t *const box_full = map_empty + kMapStages;
+    uint64_t *const box_empty = box_full + kBoxStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_xy = tiles_x * tiles_y;
+    const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMapStages; ++s) { tma::mbar_init(map_full + s, 1); tma::mbar_init(map_empty + s, kConsumers); }
+        for (int s = 0; s < kBoxStages; ++s) { tma::mbar_init(box_full + s, 1); tma::mbar_init(box_empty + s, kConsumers); }
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===== producer: warp map tiles =====
+        if (lane == 0) {
+            tma::prefetch_desc(&tp.map);
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int s = it % kMapStages, ph = (it / kMapStages) & 1;
+                tma::mbar_wait(map_empty + s, ph ^ 1);
+                const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
+                tma::mbar_arrive_expect_tx(map_full + s, kMapTileBytes);
+                if (kInter) tma::load_3d(s_map + s * kMapTileFloats, &tp.map, map_full + s, 2 * tc.w0, tc.h0, tc.n);
+                else tma::load_4d(s_map + s * kMapTileFloats, &tp.map, map_full + s, tc.w0, tc.h0, 0, tc.n);
+            }
+        }
+    } else if (warp <= kScouts) {
+        // ===== scouts (alternate tiles): map tile -> tap bounding box -> frame box load =====
+        if (lane == 0) { tma::prefetch_desc(&tp.box[0]); tma::prefetch_desc(&tp.box[1]); tma::prefetch_desc(&tp.box[2]); }
+        int it = warp - 1;
+        for (int t = blockIdx.x + (warp - 1) * gridDim.x; t < total_tiles; t += kScouts * gridDim.x, it += kScouts) {
+            const int ms = it % kMapStages, mph = (it / kMapStages) & 1;
+            const int bs = it % kBoxStages, bph = (it / kBoxStages) & 1;
+            const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
+            const int cols = min(kTW, g.Wo - tc.w0), rows = min(kTH, g.Ho - tc.h0);
+            tma::mbar_wait(map_full + ms, mph);
+            float xlo, xhi, ylo, yhi;
+            map_tile_range<kInter>(s_map + ms * kMapTileFloats, rows, cols, lane, xlo, xhi, ylo, yhi);
+            tma::mbar_wait(box_empty + bs, bph ^ 1);
+            if (lane == 0) {
+                const int4 info = box_of_range<kBorder, kAlign>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
+                s_info[bs] = info;
+                if (info.z & (kInfoFallback | kInfoEmpty)) tma::mbar_arrive(box_full + bs);
+                else {
+                    const int shape = info.z & 0xff;
+                    tma::mbar_arrive_expect_tx(box_full + bs, box_w(shape) * box_h(shape) * CS * 4);
+                    tma::load_4d(s_box + (size_t)bs * S::kBoxBytes, &tp.box[shape], box_full + bs, info.x, info.y, 0, tc.n);
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== consumers =====
+        const int cw = warp - 1 - kScouts;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int ms = it % kMapStages, mph = (it / kMapStages) & 1;
+            const int bs = it % kBoxStages, bph = (it / kBoxStages) & 1;
+            const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
+            tma::mbar_wait(map_full + ms, mph);
+            tma::mbar_wait(box_full + bs, bph);
+            const float *mp = s_map + ms * kMapTileFloats;
+            const int4 info = s_info[bs];
+            const int shape = info.z & 0xff;
+            const int pitch = box_w(shape);
+            const int plane = box_w(shape) * box_h(shape);
+            const float *bp = reinterpret_cast<const float *>(s_box + (size_t)bs * S::kBoxBytes);
+            float *__restrict__ op = (float *)out.p + (int64_t)tc.n * out.sN + (int64_t)tc.h0 * out.s2 + tc.w0;
+            const int o_ch = out.s1, o_row = out.s2;
+
+            if (info.z & kInfoInterior) {
+                const int base = -(info.y * pitch + info.x);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int r = cw * 2 + j;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int x = lane + 32 * i;
+                        float gx, gy;
+                        if (kInter) { const float2 v = *reinterpret_cast<const float2 *>(mp + r * (2 * kTW) + 2 * x); gx = v.x; gy = v.y; }
+                        else { gx = mp[r * kTW + x]; gy = mp[kTW * kTH + r * kTW + x]; }
+                        const float ix = unnorm<kAlign>(gx, Wf, Wm1), iy = unnorm<kAlign>(gy, Hf, Hm1);
+                        float x0f, y0f; int x0, y0;
+                        floor_small(ix, x0f, x0); floor_small(iy, y0f, y0);
+                        const float wx1 = fsub(ix, x0f), wx0 = fsub(x0f + 1.0f, ix);
+                        const float wy1 = fsub(iy, y0f), wy0 = fsub(y0f + 1.0f, iy);
+                        const float nw = fmul(wx0, wy0), ne = fmul(wx1, wy0), sw = fmul(wx0, wy1), se = fmul(wx1, wy1);
+                        const float *__restrict__ p0 = bp + (y0 * pitch + x0 + base);
+                        const float *__restrict__ p1 = p0 + pitch;
+                        float *__restrict__ o = op + (r * o_row + x);
+#pragma unroll
+                        for (int c = 0; c < CS; ++c) {
+                            float acc = ffma(p0[c * plane], nw, 0.f);
+                            acc = ffma(p0[c * plane + 1], ne, acc);
+                            acc = ffma(p1[c * plane], sw, acc);
+                            acc = ffma(p1[c * plane + 1], se, acc);
+                            o[c * o_ch] = acc;
+                        }
+                    }
+                }
+            } else {
+                const bool fallback = (info.z & kInfoFallback) != 0;
+                const float *__restrict__ ip = (const float *)in.p + (int64_t)tc.n * in.sN;
+                const int sH = in.s2, i_ch = in.s1;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int r = cw * 2 + j;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int x = lane + 32 * i;
+                        if (tc.h0 + r >= g.Ho || tc.w0 + x >= g.Wo) continue;
+                        float gx, gy;
+                        if (kInter) { const float2 v = *reinterpret_cast<const float2 *>(mp + r * (2 * kTW) + 2 * x); gx = v.x; gy = v.y; }
+                        else { gx = mp[r * kTW + x]; gy = mp[kTW * kTH + r * kTW + x]; }
+                        const float ix = src_index<kBorder, kAlign>(gx, g.W, Wf, Wm1);
+                        const float iy = src_index<kBorder, kAlign>(gy, g.H, Hf, Hm1);
+                        Taps<float> tp4;
+                        make_taps(ix, iy, g.H, g.W, tp4);
+                        float *__restrict__ o = op + (r * o_row + x);
+                        if (!fallback) {
+                            const float *__restrict__ p0 = bp + ((tp4.y0 - info.y) * pitch + (tp4.x0 - info.x));
+#pragma unroll
+                            for (int c = 0; c < CS; ++c) {
+                                const float *__restrict__ pc = p0 + c * plane;
+                                float acc = 0.f;
+                                if (tp4.mask & 1u) acc = ffma(pc[0], tp4.nw, acc);
+                                if (tp4.mask & 2u) acc = ffma(pc[1], tp4.ne, acc);
+                                if (tp4.mask & 4u) acc = ffma(pc[pitch], tp4.sw, acc);
+                                if (tp4.mask & 8u) acc = ffma(pc[pitch + 1], tp4.se, acc);
+                                o[c * o_ch] = acc;
+                            }
+                        } else {
+                            const float *__restrict__ p0 = ip + (tp4.y0 * sH + tp4.x0);
+#pragma unroll
+                            for (int c = 0; c < CS; ++c) {
+                                const float *__restrict__ pc = p0 + c * i_ch;
+                                float acc = 0.f;
+                                if (tp4.mask & 1u) acc = ffma(__ldg(pc), tp4.nw, acc);
+                                if (tp4.mask & 2u) acc = ffma(__ldg(pc + 1), tp4.ne, acc);
+                                if (tp4.mask & 4u) acc = ffma(__ldg(pc + sH), tp4.sw, acc);
+                                if (tp4.mask & 8u) acc = ffma(__ldg(pc + sH + 1), tp4.se, acc);
+                                o[c * o_ch] = acc;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { tma::mbar_arrive(map_empty + ms); tma::mbar_arrive(box_empty + bs); }
+        }
+    }
+}
+
+template <int CS, bool kBorder, bool kAlign, bool kInter>
+bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, int total, cudaStream_t st)
+{
+    auto kern = fwd_tma_kernel<CS, kBorder, kAlign, kInter>;
+    static bool attr_done = false;  // per instantiation
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<CS>::kTotal) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        attr_done = true;
+    }
+    const int grid = total < sm_count() ? total : sm_count();
+    kern<<<grid, kThreads, Smem<CS>::kTotal, st>>>(tp, pb.in, pb.out, pb.g, tiles_x, tiles_y, total);
+    note_launch();
+    return true;
+}
+
+template <int CS, bool kInter>
+bool launch_ba(const TmaParams &tp, const Problem &pb, int tx, int ty, int total, cudaStream_t st)
+{
+    const bool border = pb.g.padding == PWS_PAD_BORDER, align = pb.g.align != 0;
+    if (border && align) return launch_k<CS, true, true, kInter>(tp, pb, tx, ty, total, st);
+    if (border) return launch_k<CS, true, false, kInter>(tp, pb, tx, ty, total, st);
+    if (align) return launch_k<CS, false, true, kInter>(tp, pb, tx, ty, total, st);
+    return launch_k<CS, false, false, kInter>(tp, pb, tx, ty, total, st);
+}
+
+}  // namespace
+
+bool tma_disabled()
+{
+    static const bool v = [] { const char *e = std::getenv("PWS_NO_TMA"); return e && e[0] == '1'; }();
+    return v;
+}
+
+int sm_count()
+{
+    static int n[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev] = v;
+    }
+    return n[dev];
+}
+
+// Encodes the map tensor map of a TMA kernel (shared with the backward): planar maps as (Wo,Ho,2,N),
+// interleaved ones as (2Wo,Ho,N).  Returns false when the layout is neither or misaligned.
+bool encode_map_tma(const View &grid, const Geometry &g, CUtensorMap *tm, bool *inter)
+{
+    if (reinterpret_cast<uintptr_t>(grid.p) & 15) return false;
+    if (g.Wo % 4) return false;
+    if (grid.s2 == 1 && grid.s3 >= 1) {  // planar rows
+        if ((grid.s1 % 4) || (grid.s3 % 4) || (grid.sN % 4)) return false;
+        *inter = false;
+        const uint64_t dims[4] = {(uint64_t)g.Wo, (uint64_t)g.Ho, 2, (uint64_t)g.N};
+        const uint64_t sN = g.N > 1 ? (uint64_t)grid.sN : (uint64_t)grid.s3 * 2;
+        const uint64_t strides[3] = {(uint64_t)grid.s1, (uint64_t)grid.s3, sN};
+        const uint32_t box[4] = {kTW, kTH, 2, 1};
+        return tma::encode_f32(tm, grid.p, 4, dims, strides, box);
+    }
+    if (grid.s3 == 1 && grid.s2 == 2) {  // interleaved pairs
+        if ((grid.s1 % 4) || (grid.sN % 4)) return false;
+        *inter = true;
+        const uint64_t dims[3] = {(uint64_t)2 * g.Wo, (uint64_t)g.Ho, (uint64_t)g.N};
+        const uint64_t sN = g.N > 1 ? (uint64_t)grid.sN : (uint64_t)grid.s1 * g.Ho;
+        const uint64_t strides[2] = {(uint64_t)grid.s1, sN};
+        const uint32_t box[3] = {2 * kTW, kTH, 1};
+        return tma::encode_f32(tm, grid.p, 3, dims, strides, box);
+    }
+    return false;
+}
+
+// frame-shaped (W,H,C,N) fp32 tensor map with the given box
+bool encode_frame_tma(const View &v, int W, int H, int C, int N, int bw, int bh, int bc, CUtensorMap *tm)
+{
+    if (reinterpret_cast<uintptr_t>(v.p) & 15) return false;
+    if (v.s3 != 1 || (v.s2 % 4) || (v.s1 % 4) || (v.sN % 4)) return false;
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N};
+    const uint64_t s1 = C > 1 ? (uint64_t)v.s1 : (uint64_t)v.s2 * H;
+    const uint64_t sN = N > 1 ? (uint64_t)v.sN : s1 * C;
+    const uint64_t strides[3] = {(uint64_t)v.s2, s1, sN};
+    const uint32_t box[4] = {(uint32_t)bw, (uint32_t)bh, (uint32_t)bc, 1};
+    return tma::encode_f32(tm, v.p, 4, dims, strides, box);
+}
+
+// Returns true when the TMA kernel took the call.
+bool launch_forward_tma(const Problem &pb, cudaStream_t st)
+{
+    const Geometry &g = pb.g;
+    if (tma_disabled()) return false;
+    if (pb.in_dtype != PWS_F32 || pb.grid_dtype != PWS_F32) return false;
+    if (g.C != 1 && g.C != 3) return false;
+    if (pb.out.s3 != 1) return false;
+    if (g.W > (1 << 22) || g.H > (1 << 22)) return false;  // floor_small
+    const int tiles_x = (g.Wo + kTW - 1) / kTW, tiles_y = (g.Ho + kTH - 1) / kTH;
+    const int64_t total = (int64_t)tiles_x * tiles_y * g.N;
+    if (total <= 0 || total > INT_MAX) return false;
+    TmaParams tp;
+    bool inter = false;
+    if (!encode_map_tma(pb.grid, g, &tp.map, &inter)) return false;
+    for (int s = 0; s < kNumShapes; ++s)
+        if (!encode_frame_tma(pb.in, g.W, g.H, g.C, g.N, box_w(s), box_h(s), g.C, &tp.box[s])) return false;
+    if (g.C == 3) return inter ? launch_ba<3, true>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<3, false>(tp, pb, tiles_x, tiles_y, (int)total, st);
+    return inter ? launch_ba<1, true>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<1, false>(tp, pb, tiles_x, tiles_y, (int)total, st);
+}
+
+}  // namespace pws
