@@ -136,7 +136,9 @@ __device__ __forceinline__ int4 box_of_range(float xlo, float xhi, float ylo, fl
     if (!sane) return make_int4(0, 0, kInfoFallback, 0);
     int x0lo = __float2int_rd(fxlo), x0hi = __float2int_rd(fxhi);
     int y0lo = __float2int_rd(fylo), y0hi = __float2int_rd(fyhi);
-    const bool interior = x0lo >= 0 && x0hi + 1 <= W - 1 && y0lo >= 0 && y0hi + 1 <= H - 1 && full_tile;
+    // (border padding zeroes the map gradient of a coordinate sitting exactly on 0: keep such tiles masked)
+    const bool interior = x0lo >= 0 && x0hi + 1 <= W - 1 && y0lo >= 0 && y0hi + 1 <= H - 1 && full_tile &&
+                          (!kBorder || (fxlo > 0.0f && fylo > 0.0f));
     if (kBorder) {  // border padding clips the coordinate into [0, size-1] before the floor
         x0lo = clampi(x0lo, 0, W - 1); x0hi = clampi(x0hi, 0, W - 1);
         y0lo = clampi(y0lo, 0, H - 1); y0hi = clampi(y0hi, 0, H - 1);

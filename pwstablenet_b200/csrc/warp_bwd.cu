@@ -189,6 +189,10 @@ void launch_cs(const Problem &pb, unsigned blocks, int tiles_x, int tiles_y, int
 }  // namespace
 bool backward_lean_eligible(const Problem &pb);                                  // warp_bwd_lean.cu
 void launch_backward_lean(const Problem &pb, int n0, int nn, cudaStream_t st);   // warp_bwd_lean.cu
+struct BwdTmaPlan;                                                               // warp_bwd_tma.cu
+BwdTmaPlan *backward_tma_plan(const Problem &pb);
+void backward_tma_free(BwdTmaPlan *pl);
+bool launch_backward_tma(const BwdTmaPlan *pl, const Problem &pb, int n0, int nn, cudaStream_t st);
 namespace {
 
 bool force_generic()
@@ -222,6 +226,8 @@ int launch_typed(const Problem &pb, cudaStream_t st)
         if (per_chunk > g.N) per_chunk = g.N;
     }
     const bool lean = sizeof(T) == 4 && !force_generic() && backward_lean_eligible(pb);
+    BwdTmaPlan *plan = (sizeof(T) == 4 && !force_generic()) ? backward_tma_plan(pb) : nullptr;
+    struct PlanGuard { BwdTmaPlan *p; ~PlanGuard() { if (p) backward_tma_free(p); } } plan_guard{plan};
     const int cs = (g.C == 3) ? 3 : (g.C % 4 == 0) ? 4 : (g.C % 2 == 0) ? 2 : 1;
     for (int n0 = 0; n0 < g.N; n0 += per_chunk) {
         const int nn = (g.N - n0 < per_chunk) ? g.N - n0 : per_chunk;
@@ -230,6 +236,7 @@ int launch_typed(const Problem &pb, cudaStream_t st)
                                             (size_t)(frame_bytes * nn), st);
             if (e != cudaSuccess) { set_error("backward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return PWS_ECUDA; }
         }
+        if (plan && launch_backward_tma(plan, pb, n0, nn, st)) continue;
         if (lean) { launch_backward_lean(pb, n0, nn, st); continue; }
         const int64_t tiles = (int64_t)tiles_x * tiles_y * nn;
         if (tiles == 0) continue;

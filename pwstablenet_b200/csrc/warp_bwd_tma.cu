@@ -1,0 +1,496 @@
+// warp_bwd_tma.cu -- TMA-pipelined persistent backward warp (sm_100a).
+//
+// Autograd of R/main_new.py:106,116 (grad -> map) and :197 (grad -> frame), triggered at :214.
+//
+// Same pipeline as warp_fwd_tma.cu: one persistent CTA per SM walks 64x16 tiles of OUTPUT pixels;
+//   warp 0      producer   streams the tile's warp map and grad_output into shared memory (TMA);
+//   warps 1-2   scouts     (alternate tiles) reduce the map tile to the bounding box of its source taps and
+//                          load that box of the frame -- only when grad_grid is wanted, it is its one use;
+//   warps 3-10  consumers  two groups of warps, each group owning every other tile; inside a tile a
+//                          warp owns a 32-pixel-wide strip of 2*16/warps-per-group rows and marches down it.
+// The scatter into grad_input is the marching scheme of warp_bwd_lean.cu: a lane whose right neighbour
+// samples the next source pixel hands its east taps over by shuffle, the south taps ride down the strip
+// in registers, and what is left is ~1 RED.ADD.F32 per source pixel and channel on consecutive addresses.
+// The stragglers (east taps nobody takes over, parked sums whose chain broke) are compacted through a
+// per-warp queue in shared memory and leave as dense 32-lane REDs (the L2 accepts ~25 G RED
+// instructions/s whether 1 or 32 lanes are active: tools/exp/exp_red.cu).
+// grad_grid is accumulated in ATen's exact statement order from taps read out of the shared-memory box:
+// bit-identical to the other backward kernels; grad_input differs only by atomic order.
+#include "pws_pipe.cuh"
+
+#include <cstdlib>
+
+namespace pws {
+
+using namespace pipe;
+
+namespace {
+
+#ifdef PWS_EXP_NORED   // experiment: drop the scatter's atomics (results are wrong) to time everything else
+#define PWS_RED(p, v) do { if ((v) == 1.2345e-30f) *(p) = (v); } while (0)
+#else
+#define PWS_RED(p, v) atomicAdd((p), (v))
+#endif
+
+constexpr int kScouts = 2, kGroups = 2, kGroupWarps = 8, kConsumers = kGroups * kGroupWarps;
+constexpr int kThreads = (1 + kScouts + kConsumers) * 32;
+constexpr int kStripRows = 2 * kTH / kGroupWarps;  // a warp owns a 32-column strip of this many rows
+constexpr int kQueueCap = 96;  // entries per consumer warp: 31 left over + 32 lanes x 2 east taps
+
+template <int CS, bool kGgrid> struct Smem {
+    static constexpr int kInStages = kGgrid ? 4 : 6;
+    static constexpr int kInfoStages = 4;
+    static constexpr int kBoxStages = kGgrid ? kInfoStages : 0;
+    static constexpr int kInBytes = kMapTileBytes + CS * kTW * kTH * 4;
+    static constexpr int kBoxBytes = kMaxBW * kMaxBH * CS * 4;
+    static constexpr int kInOff = 0;
+    static constexpr int kBoxOff = kInStages * kInBytes;
+    static constexpr int kQueueOff = kBoxOff + kBoxStages * kBoxBytes;
+    static constexpr int kQueueEntry = CS == 3 ? 16 : 8;
+    static constexpr int kInfoOff = kQueueOff + kConsumers * kQueueCap * kQueueEntry;
+    static constexpr int kBarOff = kInfoOff + kInfoStages * 32;
+    static constexpr int kTotal = kBarOff + (2 * kInStages + 2 * kInfoStages) * 8;
+    static_assert(kInBytes % 128 == 0 && kBoxBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(kTotal <= 227 * 1024, "shared memory budget");
+    static_assert(kInStages % kGroups == 0 && kInfoStages % kGroups == 0, "a stage must always belong to the same consumer group");
+};
+
+struct TmaParams {
+    CUtensorMap map;              // as in warp_fwd_tma.cu
+    CUtensorMap gout;             // (Wo, Ho, C, N), box (64,16,CS,1)
+    CUtensorMap box[kNumShapes];  // frame (W, H, C, N), box (BW, BH, CS, 1)
+};
+
+template <int CS>
+struct Carry {
+    int x, y;  // target of the parked south-west sums
+    bool live;
+    float v[CS];
+};
+
+// Straggler queue of a consumer warp: one entry = a source pixel offset plus its CS channel values.
+template <int CS> struct QEntry;
+template <> struct QEntry<1> { int off; float v[1]; };
+template <> struct QEntry<3> { int off; float v[3]; };
+template <int CS>
+struct Queue {
+    QEntry<CS> *buf;  // shared memory, kQueueCap entries
+    int count;        // warp-uniform
+};
+
+template <int CS>
+__device__ __forceinline__ void queue_put(Queue<CS> &q, int pos, int off, const float (&v)[CS])
+{
+    if (CS == 3) *reinterpret_cast<int4 *>(q.buf + pos) = make_int4(off, __float_as_int(v[0]), __float_as_int(v[CS > 1 ? 1 : 0]), __float_as_int(v[CS > 2 ? 2 : 0]));
+    else *reinterpret_cast<int2 *>(q.buf + pos) = make_int2(off, __float_as_int(v[0]));
+}
+template <int CS>
+__device__ __forceinline__ void queue_pop_red(const Queue<CS> &q, int pos, float *const (&gipk)[CS])
+{
+    if (CS == 3) {
+        const int4 e = *reinterpret_cast<const int4 *>(q.buf + pos);
+        PWS_RED(gipk[0] + e.x, __int_as_float(e.y));
+        PWS_RED(gipk[CS > 1 ? 1 : 0] + e.x, __int_as_float(e.z));
+        PWS_RED(gipk[CS > 2 ? 2 : 0] + e.x, __int_as_float(e.w));
+    } else {
+        const int2 e = *reinterpret_cast<const int2 *>(q.buf + pos);
+        PWS_RED(gipk[0] + e.x, __int_as_float(e.y));
+    }
+}
+// dense 32-lane REDs while at least a warp's worth of entries is queued
+template <int CS>
+__device__ __forceinline__ void queue_drain(Queue<CS> &q, float *const (&gipk)[CS], int lane)
+{
+    __syncwarp();
+#pragma unroll 1
+    while (q.count >= 32) {
+        queue_pop_red<CS>(q, q.count - 32 + lane, gipk);
+        q.count -= 32;
+    }
+    __syncwarp();
+}
+template <int CS>
+__device__ __forceinline__ void queue_flush(Queue<CS> &q, float *const (&gipk)[CS], int lane)
+{
+    queue_drain<CS>(q, gipk, lane);
+    if (lane < q.count) queue_pop_red<CS>(q, lane, gipk);
+    q.count = 0;
+    __syncwarp();
+}
+
+// One output row (32 pixels) of a warp.  kMasked=false: every lane is a real pixel with 4 valid taps.
+// kBoxTaps: the taps of grad_grid come from the shared-memory box (tap = box[(y - by) * pitch + (x - bx)] per plane).
+template <int CS, bool kGin, bool kGgrid, bool kMasked, bool kBoxTaps>
+__device__ __forceinline__ void bwd_row(
+    const int lane, const bool px_ok, const unsigned live,
+    const float ix, const float iy, const float x0f, const float y0f, const int x0, const int y0,
+    const float gxm, const float gym, const float (&go)[CS],
+    const float *__restrict__ box, const int pitch, const int plane,
+    const float *__restrict__ ip, const int sH, const int i_ch, const int H, const int W,
+    float *const (&gipk)[CS],
+    float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy, Queue<CS> &q)
+{
+    const float dw = fsub(x0f + 1.0f, ix), de = fsub(ix, x0f), dn = fsub(y0f + 1.0f, iy), ds = fsub(iy, y0f);
+    unsigned mask = 15u;
+    if (kMasked) {
+        const bool xw = (unsigned)x0 < (unsigned)W, xe = (unsigned)(x0 + 1) < (unsigned)W;
+        const bool yn = (unsigned)y0 < (unsigned)H, ys = (unsigned)(y0 + 1) < (unsigned)H;
+        mask = ((xw && yn) ? 1u : 0u) | ((xe && yn) ? 2u : 0u) | ((xw && ys) ? 4u : 0u) | ((xe && ys) ? 8u : 0u);
+        if (!px_ok) mask = 0u;
+    }
+
+    if (kGgrid && (!kMasked || px_ok)) {
+        float gix = 0.f, giy = 0.f;
+        const float *__restrict__ p0 = kBoxTaps ? box + (y0 * pitch + x0) : ip + (y0 * sH + x0);
+        const int row = kBoxTaps ? pitch : sH, ch = kBoxTaps ? plane : i_ch;
+#pragma unroll
+        for (int k = 0; k < CS; ++k) {
+            const float *__restrict__ pc = p0 + k * ch;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+            if (kBoxTaps) {
+                if (!kMasked || (mask & 1u)) v0 = pc[0];
+                if (!kMasked || (mask & 2u)) v1 = pc[1];
+                if (!kMasked || (mask & 4u)) v2 = pc[row];
+                if (!kMasked || (mask & 8u)) v3 = pc[row + 1];
+            } else {
+                if (!kMasked || (mask & 1u)) v0 = __ldg(pc);
+                if (!kMasked || (mask & 2u)) v1 = __ldg(pc + 1);
+                if (!kMasked || (mask & 4u)) v2 = __ldg(pc + row);
+                if (!kMasked || (mask & 8u)) v3 = __ldg(pc + row + 1);
+            }
+            // ATen's statement order: t = v*d rounded, then one fma with gOut
+            if (!kMasked || (mask & 1u)) { gix = ffma(-fmul(v0, dn), go[k], gix); giy = ffma(-fmul(v0, dw), go[k], giy); }
+            if (!kMasked || (mask & 2u)) { gix = ffma(fmul(v1, dn), go[k], gix);  giy = ffma(-fmul(v1, de), go[k], giy); }
+            if (!kMasked || (mask & 4u)) { gix = ffma(-fmul(v2, ds), go[k], gix); giy = ffma(fmul(v2, dw), go[k], giy); }
+            if (!kMasked || (mask & 8u)) { gix = ffma(fmul(v3, ds), go[k], gix);  giy = ffma(fmul(v3, de), go[k], giy); }
+        }
+        gix = fmul(gxm, gix); giy = fmul(gym, giy);
+        if (gg_s3 == 1) *reinterpret_cast<float2 *>(ggq) = make_float2(gix, giy);
+        else { ggq[0] = gix; ggq[gg_s3] = giy; }
+    }
+
+    if (kGin) {
+        const float nw = fmul(dw, dn), ne = fmul(de, dn), sw = fmul(dw, ds), se = fmul(de, ds);
+        const int px0 = __shfl_up_sync(0xffffffffu, x0, 1), py0 = __shfl_up_sync(0xffffffffu, y0, 1);
+        const int nx0 = __shfl_down_sync(0xffffffffu, x0, 1), ny0 = __shfl_down_sync(0xffffffffu, y0, 1);
+        bool take = lane > 0 && px0 + 1 == x0 && py0 == y0;
+        bool given = lane < 31 && nx0 == x0 + 1 && ny0 == y0;
+        if (kMasked) {
+            take = take && px_ok && ((live >> (lane - 1)) & 1u);
+            given = given && px_ok && ((live >> (lane + 1)) & 1u);
+        }
+        const bool chain = cy.live && cy.x == x0 && cy.y == y0;
+        const int o_nw = y0 * W + x0;  // grad_input is dense NCHW
+        const int o_cy = cy.y * W + cy.x;
+        // stragglers of this row -> queue: east taps nobody takes over (top and bottom), parked sums whose chain broke
+        const bool p_e1 = !given && (mask & 2u), p_e2 = !given && (mask & 8u), p_f = cy.live && !chain;
+        const unsigned lt = (1u << lane) - 1u;
+        float etop[CS], ebot[CS], brk[CS];
+#pragma unroll
+        for (int k = 0; k < CS; ++k) {
+            float top = fmul(nw, go[k]), bot = fmul(sw, go[k]);
+            etop[k] = fmul(ne, go[k]); ebot[k] = fmul(se, go[k]);
+            const float ptop = __shfl_up_sync(0xffffffffu, etop[k], 1), pbot = __shfl_up_sync(0xffffffffu, ebot[k], 1);
+            if (take) { top += ptop; bot += pbot; }
+            brk[k] = cy.v[k];
+            if (chain) top += cy.v[k];
+            if (mask & 1u) PWS_RED(gipk[k] + o_nw, top);
+            cy.v[k] = bot;
+        }
+        if (!kMasked) {
+            // all taps valid: the two east classes share their predicate
+            const unsigned b = __ballot_sync(0xffffffffu, p_e1);
+            if (b) {
+                const int n = __popc(b), pos = q.count + __popc(b & lt);
+                if (p_e1) { queue_put<CS>(q, pos, o_nw + 1, etop); queue_put<CS>(q, pos + n, o_nw + W + 1, ebot); }
+                q.count += 2 * n;
+                if (q.count >= 32) queue_drain<CS>(q, gipk, lane);
+            }
+        } else {
+            const unsigned b1 = __ballot_sync(0xffffffffu, p_e1), b2 = __ballot_sync(0xffffffffu, p_e2);
+            if (b1 | b2) {
+                const int n1 = __popc(b1), pos1 = q.count + __popc(b1 & lt), pos2 = q.count + n1 + __popc(b2 & lt);
+                if (p_e1) queue_put<CS>(q, pos1, o_nw + 1, etop);
+                if (p_e2) queue_put<CS>(q, pos2, o_nw + W + 1, ebot);
+                q.count += n1 + __popc(b2);
+                if (q.count >= 32) queue_drain<CS>(q, gipk, lane);
+            }
+        }
+        {
+            const unsigned b = __ballot_sync(0xffffffffu, p_f);
+            if (b) {
+                const int pos = q.count + __popc(b & lt);
+                if (p_f) queue_put<CS>(q, pos, o_cy, brk);
+                q.count += __popc(b);
+                if (q.count >= 32) queue_drain<CS>(q, gipk, lane);
+            }
+        }
+        cy.x = x0; cy.y = y0 + 1;
+        cy.live = (mask & 4u) != 0u;
+    }
+}
+
+// A strip of a tile that is not "interior" (frame border, partial tile, fallback): the masked bodies.
+template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
+__device__ __forceinline__ void masked_strip(
+    const int lane, const int4 info, const int h0, const int w0, const int row0, const int col0,
+    const float *__restrict__ mp, const float *__restrict__ gop, const float *__restrict__ bp, const int pitch, const int plane,
+    const float *__restrict__ ip, const int sH, const int i_ch, const Geometry g,
+    float *const (&gipk)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Carry<CS> &cy, Queue<CS> &q)
+{
+    const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
+    const bool col_ok = w0 + lane < g.Wo;
+    const unsigned live = __ballot_sync(0xffffffffu, col_ok);
+    const bool box_taps = kGgrid && !(info.z & (kInfoFallback | kInfoEmpty));
+    const int rows = min(kStripRows, g.Ho - h0);  // may be <= 0 for the strips below the last row
+    for (int r = 0; r < rows; ++r) {
+        float gx, gy, go[CS];
+        if (kInter) { const float2 v = *reinterpret_cast<const float2 *>(mp + (row0 + r) * (2 * kTW) + 2 * (col0 + lane)); gx = v.x; gy = v.y; }
+        else { gx = mp[(row0 + r) * kTW + col0 + lane]; gy = mp[kTW * kTH + (row0 + r) * kTW + col0 + lane]; }
+#pragma unroll
+        for (int k = 0; k < CS; ++k) go[k] = gop[k * (kTW * kTH) + r * kTW];
+        float gxm, gym;
+        const float ix = src_index_grad<kBorder, kAlign>(gx, Wf, Wm1, &gxm);
+        const float iy = src_index_grad<kBorder, kAlign>(gy, Hf, Hm1, &gym);
+        const float x0f = floorf(ix), y0f = floorf(iy);
+        const int x0 = (int)x0f, y0 = (int)y0f;
+        if (box_taps)
+            bwd_row<CS, kGin, kGgrid, true, true>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
+                                                   bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gipk, ggq, gg_s3, cy, q);
+        else
+            bwd_row<CS, kGin, kGgrid, true, false>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
+                                                    bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gipk, ggq, gg_s3, cy, q);
+        if (kGgrid) ggq += gg_s1;
+    }
+}
+
+template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
+__global__ void __launch_bounds__(kThreads, 1)
+bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View gin, const View ggrid, const Geometry g,
+               const int tiles_x, const int tiles_y, const int total_tiles, const int n_begin)
+{
+    using S = Smem<CS, kGgrid>;
+    constexpr int kInStages = S::kInStages, kInfoStages = S::kInfoStages;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *const s_in = smem + S::kInOff;
+    unsigned char *const s_box = smem + S::kBoxOff;
+    QEntry<CS> *const s_queue = reinterpret_cast<QEntry<CS> *>(smem + S::kQueueOff);
+    int4 *const s_info = reinterpret_cast<int4 *>(smem + S::kInfoOff);
+    uint64_t *const in_full = reinterpret_cast<uint64_t *>(smem + S::kBarOff);
+    uint64_t *const in_empty = in_full + kInStages;
+    uint64_t *const box_full = in_empty + kInStages;
+    uint64_t *const box_empty = box_full + kInfoStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_xy = tiles_x * tiles_y;
+    const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kInStages; ++s) { tma::mbar_init(in_full + s, 1); tma::mbar_init(in_empty + s, kGroupWarps); }
+        for (int s = 0; s < kInfoStages; ++s) { tma::mbar_init(box_full + s, 1); tma::mbar_init(box_empty + s, kGroupWarps); }
+        tma::fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===== producer: warp map + grad_output tiles =====
+        if (lane == 0) {
+            tma::prefetch_desc(&tp.map); tma::prefetch_desc(&tp.gout);
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int s = it % kInStages, ph = (it / kInStages) & 1;
+                tma::mbar_wait_relaxed(in_empty + s, ph ^ 1);
+                const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
+                float *dst = reinterpret_cast<float *>(s_in + (size_t)s * S::kInBytes);
+                tma::mbar_arrive_expect_tx(in_full + s, S::kInBytes);
+                if (kInter) tma::load_3d(dst, &tp.map, in_full + s, 2 * tc.w0, tc.h0, n_begin + tc.n);
+                else tma::load_4d(dst, &tp.map, in_full + s, tc.w0, tc.h0, 0, n_begin + tc.n);
+                tma::load_4d(dst + kMapTileFloats, &tp.gout, in_full + s, tc.w0, tc.h0, 0, n_begin + tc.n);
+            }
+        }
+    } else if (warp <= kScouts) {
+        // ===== scouts (alternate tiles): map tile -> tap bounding box -> frame box load =====
+        if (kGgrid && lane == 0) { tma::prefetch_desc(&tp.box[0]); tma::prefetch_desc(&tp.box[1]); tma::prefetch_desc(&tp.box[2]); }
+        int it = warp - 1;
+        for (int t = blockIdx.x + (warp - 1) * gridDim.x; t < total_tiles; t += kScouts * gridDim.x, it += kScouts) {
+            const int is = it % kInStages, iph = (it / kInStages) & 1;
+            const int bs = it % kInfoStages, bph = (it / kInfoStages) & 1;
+            const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
+            const int cols = min(kTW, g.Wo - tc.w0), rows = min(kTH, g.Ho - tc.h0);
+            tma::mbar_wait_relaxed(in_full + is, iph);
+            float xlo, xhi, ylo, yhi;
+            map_tile_range<kInter>(reinterpret_cast<const float *>(s_in + (size_t)is * S::kInBytes), rows, cols, lane, xlo, xhi, ylo, yhi);
+            tma::mbar_wait_relaxed(box_empty + bs, bph ^ 1);
+            if (lane == 0) {
+                int4 info = box_of_range<kBorder, kAlign>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
+                info.w = tc.n;
+                s_info[2 * bs] = info;
+                s_info[2 * bs + 1] = make_int4(tc.h0, tc.w0, 0, 0);
+                if (!kGgrid || (info.z & (kInfoFallback | kInfoEmpty))) tma::mbar_arrive(box_full + bs);
+                else {
+                    const int shape = info.z & 0xff;
+                    tma::mbar_arrive_expect_tx(box_full + bs, box_w(shape) * box_h(shape) * CS * 4);
+                    tma::load_4d(s_box + (size_t)bs * S::kBoxBytes, &tp.box[shape], box_full + bs, info.x, info.y, 0, n_begin + tc.n);
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== consumers: group `grp` owns tiles it = grp, grp + 2, ...; a warp owns a 32 x 8 strip =====
+        const int cw = warp - 1 - kScouts, grp = cw / kGroupWarps, wg = cw % kGroupWarps;
+        const int col0 = (wg & 1) * 32, row0 = (wg >> 1) * kStripRows;
+        Queue<CS> q;
+        q.buf = s_queue + cw * kQueueCap;
+        q.count = 0;
+        const float gxm_in = (kAlign ? Wm1 : Wf) * 0.5f, gym_in = (kAlign ? Hm1 : Hf) * 0.5f;
+        int it = grp;
+        for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += kGroups * gridDim.x, it += kGroups) {
+            const int is = it % kInStages, iph = (it / kInStages) & 1;
+            const int bs = it % kInfoStages, bph = (it / kInfoStages) & 1;
+            tma::mbar_wait(in_full + is, iph);
+            tma::mbar_wait(box_full + bs, bph);
+            const int4 info = s_info[2 * bs], where = s_info[2 * bs + 1];
+            const int n = n_begin + info.w, h0 = where.x + row0, w0 = where.y + col0;
+            const int shape = info.z & 0xff;
+            const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
+            const float *mp = reinterpret_cast<const float *>(s_in + (size_t)is * S::kInBytes);
+            const float *gop = mp + kMapTileFloats + row0 * kTW + col0 + lane;
+            const float *bp = reinterpret_cast<const float *>(s_box + (size_t)bs * S::kBoxBytes) - (info.y * pitch + info.x);
+            const float *__restrict__ ip = (const float *)in.p + (int64_t)n * in.sN;
+            float *gipk[CS];  // per-channel planes of this frame's grad_input (dense NCHW)
+#pragma unroll
+            for (int k = 0; k < CS; ++k) gipk[k] = kGin ? (float *)gin.p + ((int64_t)n * gin.sN + (int64_t)k * gin.s1) : nullptr;
+            float *__restrict__ ggq = kGgrid ? (float *)ggrid.p + (int64_t)n * ggrid.sN + (int64_t)h0 * ggrid.s1 + (int64_t)(w0 + lane) * ggrid.s2 : nullptr;
+
+            Carry<CS> cy;
+            cy.x = 0; cy.y = 0; cy.live = false;
+#pragma unroll
+            for (int k = 0; k < CS; ++k) cy.v[k] = 0.f;
+
+            if (info.z & kInfoInterior) {
+#pragma unroll 2
+                for (int r = 0; r < kStripRows; ++r) {
+                    float gx, gy, go[CS];
+                    if (kInter) { const float2 v = *reinterpret_cast<const float2 *>(mp + (row0 + r) * (2 * kTW) + 2 * (col0 + lane)); gx = v.x; gy = v.y; }
+                    else { gx = mp[(row0 + r) * kTW + col0 + lane]; gy = mp[kTW * kTH + (row0 + r) * kTW + col0 + lane]; }
+#pragma unroll
+                    for (int k = 0; k < CS; ++k) go[k] = gop[k * (kTW * kTH) + r * kTW];
+                    const float ix = unnorm<kAlign>(gx, Wf, Wm1), iy = unnorm<kAlign>(gy, Hf, Hm1);
+                    float x0f, y0f; int x0, y0;
+                    floor_small(ix, x0f, x0); floor_small(iy, y0f, y0);
+                    bwd_row<CS, kGin, kGgrid, false, true>(lane, true, 0xffffffffu, ix, iy, x0f, y0f, x0, y0, gxm_in, gym_in, go,
+                                                            bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gipk, ggq, ggrid.s3, cy, q);
+                    if (kGgrid) ggq += ggrid.s1;
+                }
+            } else {
+                masked_strip<CS, kBorder, kAlign, kInter, kGin, kGgrid>(lane, info, h0, w0, row0, col0, mp, gop, bp, pitch, plane, ip, in.s2, in.s1,
+                                                                        g, gipk, ggq, ggrid.s1, ggrid.s3, cy, q);
+            }
+            if (kGin) {
+                if (cy.live) {
+                    const int o_cy = cy.y * g.W + cy.x;
+#pragma unroll
+                    for (int k = 0; k < CS; ++k) PWS_RED(gipk[k] + o_cy, cy.v[k]);
+                }
+                queue_flush<CS>(q, gipk, lane);
+            }
+            __syncwarp();
+            if (lane == 0) { tma::mbar_arrive(in_empty + is); tma::mbar_arrive(box_empty + bs); }
+        }
+    }
+}
+
+template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
+bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, int total, int n0, cudaStream_t st)
+{
+    auto kern = bwd_tma_kernel<CS, kBorder, kAlign, kInter, kGin, kGgrid>;
+    using S = Smem<CS, kGgrid>;
+    static bool attr_done = false;  // per instantiation
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        attr_done = true;
+    }
+    const int grid = total < sm_count() ? total : sm_count();
+    kern<<<grid, kThreads, S::kTotal, st>>>(tp, pb.in, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0);
+    note_launch();
+    return true;
+}
+
+template <int CS, bool kBorder, bool kAlign, bool kInter>
+bool launch_mask(const TmaParams &tp, const Problem &pb, int tx, int ty, int total, int n0, cudaStream_t st)
+{
+    if (pb.want_gin && pb.want_ggrid) return launch_k<CS, kBorder, kAlign, kInter, true, true>(tp, pb, tx, ty, total, n0, st);
+    if (pb.want_gin) return launch_k<CS, kBorder, kAlign, kInter, true, false>(tp, pb, tx, ty, total, n0, st);
+    return launch_k<CS, kBorder, kAlign, kInter, false, true>(tp, pb, tx, ty, total, n0, st);
+}
+
+template <int CS, bool kInter>
+bool launch_ba(const TmaParams &tp, const Problem &pb, int tx, int ty, int total, int n0, cudaStream_t st)
+{
+    const bool border = pb.g.padding == PWS_PAD_BORDER, align = pb.g.align != 0;
+    if (border && align) return launch_mask<CS, true, true, kInter>(tp, pb, tx, ty, total, n0, st);
+    if (border) return launch_mask<CS, true, false, kInter>(tp, pb, tx, ty, total, n0, st);
+    if (align) return launch_mask<CS, false, true, kInter>(tp, pb, tx, ty, total, n0, st);
+    return launch_mask<CS, false, false, kInter>(tp, pb, tx, ty, total, n0, st);
+}
+
+}  // namespace
+
+// Prepared launch state of an eligible problem (tensor maps are encoded once per call, not per chunk).
+struct BwdTmaPlan {
+    TmaParams tp;
+    bool inter;
+    int tiles_x, tiles_y;
+};
+
+// Returns a heap plan when the TMA backward can take the problem, nullptr otherwise.
+BwdTmaPlan *backward_tma_plan(const Problem &pb)
+{
+    const Geometry &g = pb.g;
+    if (tma_disabled()) return nullptr;
+    if (pb.in_dtype != PWS_F32 || pb.grid_dtype != PWS_F32) return nullptr;
+    if (g.C != 1 && g.C != 3) return nullptr;
+    if (g.W > (1 << 22) || g.H > (1 << 22)) return nullptr;
+    if (pb.want_gin && !(pb.gin.s3 == 1 && pb.gin.s2 == g.W && pb.gin.s1 == g.W * g.H)) return nullptr;
+    if (pb.want_ggrid) {
+        // written with plain stores: planar (two scalars) or interleaved (one float2)
+        if (pb.ggrid.s3 == 1 && ((reinterpret_cast<uintptr_t>(pb.ggrid.p) & 7) || (pb.ggrid.sN & 1) || (pb.ggrid.s1 & 1) || (pb.ggrid.s2 & 1)))
+            return nullptr;
+    }
+    BwdTmaPlan *pl = new BwdTmaPlan;
+    pl->tiles_x = (g.Wo + kTW - 1) / kTW;
+    pl->tiles_y = (g.Ho + kTH - 1) / kTH;
+    bool ok = encode_map_tma(pb.grid, g, &pl->tp.map, &pl->inter);
+    ok = ok && encode_frame_tma(pb.gout, g.Wo, g.Ho, g.C, g.N, kTW, kTH, g.C, &pl->tp.gout);
+    for (int s = 0; ok && s < kNumShapes; ++s) ok = encode_frame_tma(pb.in, g.W, g.H, g.C, g.N, box_w(s), box_h(s), g.C, &pl->tp.box[s]);
+    if ((int64_t)pl->tiles_x * pl->tiles_y * g.N > INT_MAX) ok = false;
+    if (!ok) { delete pl; return nullptr; }
+    return pl;
+}
+
+void backward_tma_free(BwdTmaPlan *pl) { delete pl; }
+
+// Launch frames [n0, n0+nn).
+bool launch_backward_tma(const BwdTmaPlan *pl, const Problem &pb, int n0, int nn, cudaStream_t st)
+{
+    const int total = pl->tiles_x * pl->tiles_y * nn;
+    if (total <= 0) return true;
+    static const bool alias = [] { const char *e = std::getenv("PWS_EXP_GIN_ALIAS"); return e && e[0] == '1'; }();
+    if (alias) {  // experiment: every frame scatters into frame 0's grad_input (L2-resident footprint; results are wrong)
+        Problem p2 = pb;
+        p2.gin.sN = 0;
+        if (pb.g.C == 3)
+            return pl->inter ? launch_ba<3, true>(pl->tp, p2, pl->tiles_x, pl->tiles_y, total, n0, st)
+                             : launch_ba<3, false>(pl->tp, p2, pl->tiles_x, pl->tiles_y, total, n0, st);
+    }
+    if (pb.g.C == 3)
+        return pl->inter ? launch_ba<3, true>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st)
+                         : launch_ba<3, false>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st);
+    return pl->inter ? launch_ba<1, true>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st)
+                     : launch_ba<1, false>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st);
+}
+
+}  // namespace pws

@@ -26,17 +26,19 @@ using namespace pipe;
 
 namespace {
 
-constexpr int kScouts = 2, kConsumers = 8, kThreads = (1 + kScouts + kConsumers) * 32;
-constexpr int kMapStages = 6, kBoxStages = 5;
+constexpr int kScouts = 2, kGroups = 2, kGroupWarps = 8, kConsumers = kGroups * kGroupWarps;
+constexpr int kThreads = (1 + kScouts + kConsumers) * 32;
+constexpr int kMapStages = 6, kBoxStages = 4;
 
 template <int CS> struct Smem {
     static constexpr int kBoxBytes = kMaxBW * kMaxBH * CS * 4;
     static constexpr int kMapOff = 0;
     static constexpr int kBoxOff = kMapStages * kMapTileBytes;
     static constexpr int kInfoOff = kBoxOff + kBoxStages * kBoxBytes;
-    static constexpr int kBarOff = kInfoOff + kBoxStages * 16;
+    static constexpr int kBarOff = kInfoOff + kBoxStages * 32;
     static constexpr int kTotal = kBarOff + (2 * kMapStages + 2 * kBoxStages) * 8;
     static_assert(kBoxBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(kMapStages % kGroups == 0 && kBoxStages % kGroups == 0, "a stage must always belong to the same consumer group");
 };
 
 struct TmaParams {
@@ -64,8 +66,8 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
     const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kMapStages; ++s) { tma::mbar_init(map_full + s, 1); tma::mbar_init(map_empty + s, kConsumers); }
-        for (int s = 0; s < kBoxStages; ++s) { tma::mbar_init(box_full + s, 1); tma::mbar_init(box_empty + s, kConsumers); }
+        for (int s = 0; s < kMapStages; ++s) { tma::mbar_init(map_full + s, 1); tma::mbar_init(map_empty + s, kGroupWarps); }
+        for (int s = 0; s < kBoxStages; ++s) { tma::mbar_init(box_full + s, 1); tma::mbar_init(box_empty + s, kGroupWarps); }
         tma::fence_barrier_init();
     }
     __syncthreads();
@@ -77,7 +79,7 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
             int it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const int s = it % kMapStages, ph = (it / kMapStages) & 1;
-                tma::mbar_wait(map_empty + s, ph ^ 1);
+                tma::mbar_wait_relaxed(map_empty + s, ph ^ 1);
                 const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
                 tma::mbar_arrive_expect_tx(map_full + s, kMapTileBytes);
                 if (kInter) tma::load_3d(s_map + s * kMapTileFloats, &tp.map, map_full + s, 2 * tc.w0, tc.h0, tc.n);
@@ -93,13 +95,15 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
             const int bs = it % kBoxStages, bph = (it / kBoxStages) & 1;
             const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
             const int cols = min(kTW, g.Wo - tc.w0), rows = min(kTH, g.Ho - tc.h0);
-            tma::mbar_wait(map_full + ms, mph);
+            tma::mbar_wait_relaxed(map_full + ms, mph);
             float xlo, xhi, ylo, yhi;
             map_tile_range<kInter>(s_map + ms * kMapTileFloats, rows, cols, lane, xlo, xhi, ylo, yhi);
-            tma::mbar_wait(box_empty + bs, bph ^ 1);
+            tma::mbar_wait_relaxed(box_empty + bs, bph ^ 1);
             if (lane == 0) {
-                const int4 info = box_of_range<kBorder, kAlign>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
-                s_info[bs] = info;
+                int4 info = box_of_range<kBorder, kAlign>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
+                info.w = tc.n;
+                s_info[2 * bs] = info;
+                s_info[2 * bs + 1] = make_int4(tc.h0, tc.w0, 0, 0);
                 if (info.z & (kInfoFallback | kInfoEmpty)) tma::mbar_arrive(box_full + bs);
                 else {
                     const int shape = info.z & 0xff;
@@ -111,16 +115,17 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
         }
     } else {
         // ===== consumers =====
-        const int cw = warp - 1 - kScouts;
-        int it = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int cw = warp - 1 - kScouts, grp = cw / kGroupWarps, wg = cw % kGroupWarps;
+        int it = grp;
+        for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += kGroups * gridDim.x, it += kGroups) {
             const int ms = it % kMapStages, mph = (it / kMapStages) & 1;
             const int bs = it % kBoxStages, bph = (it / kBoxStages) & 1;
-            const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
             tma::mbar_wait(map_full + ms, mph);
             tma::mbar_wait(box_full + bs, bph);
             const float *mp = s_map + ms * kMapTileFloats;
-            const int4 info = s_info[bs];
+            const int4 info = s_info[2 * bs], where = s_info[2 * bs + 1];
+            TileCoord tc;
+            tc.n = info.w; tc.h0 = where.x; tc.w0 = where.y;
             const int shape = info.z & 0xff;
             const int pitch = box_w(shape);
             const int plane = box_w(shape) * box_h(shape);
@@ -132,7 +137,7 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
                 const int base = -(info.y * pitch + info.x);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int r = cw * 2 + j;
+                    const int r = wg * 2 + j;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int x = lane + 32 * i;
@@ -164,7 +169,7 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
                 const int sH = in.s2, i_ch = in.s1;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int r = cw * 2 + j;
+                    const int r = wg * 2 + j;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int x = lane + 32 * i;

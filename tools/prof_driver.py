@@ -20,5 +20,8 @@ gout = torch.rand(N, 3, H, W, device="cuda")
 for _ in range(iters):
     out = pw.warp2d_forward(frames, grid, 0, False)
     gin, gg = pw.warp2d_backward(gout, frames, grid, 0, False, (True, True))
+    if os.environ.get("PROF_SPLIT"):
+        pw.warp2d_backward(gout, frames, grid, 0, False, (True, False))
+        pw.warp2d_backward(gout, frames, grid, 0, False, (False, True))
 torch.cuda.synchronize()
 print("done", float(out.sum()), float(gin.sum()))

@@ -27,3 +27,32 @@ for (N, C, H, W) in cases:
                         d = (out - ref).abs()
                         print("MISMATCH", (N, C, H, W), kind, align, pad, layout, "max", float(d.max()), "count", int((d > 0).sum()))
 print("forward check done, mismatches:", bad)
+
+# ---- backward: grad_grid bit-exact vs ATen is not guaranteed (ATen uses its own order), compare with tolerance;
+# grad_input within 1e-4 relative of ATen
+bad = 0
+for (N, C, H, W) in cases:
+    for kind in kinds:
+        for align in (False, True):
+            for pad in (0, 1):
+                for layout in ("planar", "inter"):
+                    g = torch.from_numpy(synth.make_map(kind, N, H, W, align, seed=3)).cuda()
+                    if layout == "planar":
+                        g = g.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+                    fr = torch.rand(N, C, H, W, device="cuda") * 255
+                    go = torch.rand(N, C, H, W, device="cuda")
+                    for mask in ((True, True), (True, False), (False, True)):
+                        gi, gg = pw.warp2d_backward(go, fr, g, pad, align, mask)
+                        ri, rg = torch.ops.aten.grid_sampler_2d_backward(go, fr, g, 0, pad, align, list(mask))
+                        torch.cuda.synchronize()
+                        msgs = []
+                        if mask[0]:
+                            err = float((gi - ri).abs().max() / ri.abs().max().clamp_min(1e-30))
+                            if not err < 1e-4: msgs.append(f"gin rel {err:.3e}")
+                        if mask[1]:
+                            err = float((gg - rg).abs().max() / rg.abs().max().clamp_min(1e-30))
+                            if not err < 1e-5: msgs.append(f"ggrid rel {err:.3e}")
+                        if msgs:
+                            bad += 1
+                            print("MISMATCH", (N, C, H, W), kind, align, pad, layout, mask, *msgs)
+print("backward check done, mismatches:", bad)
