@@ -79,6 +79,54 @@ __device__ __forceinline__ void load_2d(void *dst, const CUtensorMap *tm, uint64
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// ---- L2 eviction priorities ------------------------------------------------------------------
+// Streaming operands are loaded evict_first, accumulators that are revisited (grad_input between its
+// zero-fill and its last RED) are written evict_last, so the stream does not push them out of L2.
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void load_3d_hint(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void load_4d_hint(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2, int c3, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void st_f32_hint(float *p, float v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_zero_v4_hint(float4 *p, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %1, %1, %1}, %2;" ::"l"(p), "f"(0.0f), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_f32_hint(float *p, float v, uint64_t pol)
+{
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol));
+}
+
 // shared -> global box store / f32 add-reduction (out-of-range elements are dropped); bulk-group completion
 __device__ __forceinline__ void store_3d(const CUtensorMap *tm, const void *src, int c0, int c1, int c2)
 {

@@ -193,6 +193,7 @@ struct BwdTmaPlan;                                                              
 BwdTmaPlan *backward_tma_plan(const Problem &pb);
 void backward_tma_free(BwdTmaPlan *pl);
 bool launch_backward_tma(const BwdTmaPlan *pl, const Problem &pb, int n0, int nn, cudaStream_t st);
+int backward_tma_max_frames();
 namespace {
 
 bool force_generic()
@@ -229,6 +230,14 @@ int launch_typed(const Problem &pb, cudaStream_t st)
     BwdTmaPlan *plan = (sizeof(T) == 4 && !force_generic()) ? backward_tma_plan(pb) : nullptr;
     struct PlanGuard { BwdTmaPlan *p; ~PlanGuard() { if (p) backward_tma_free(p); } } plan_guard{plan};
     const int cs = (g.C == 3) ? 3 : (g.C % 4 == 0) ? 4 : (g.C % 2 == 0) ? 2 : 1;
+    if (plan) {
+        // the TMA kernel zero-fills grad_input itself (two frames ahead of its scatter): no memset pass
+        const int step = backward_tma_max_frames();
+        bool ok = true;
+        for (int n0 = 0; ok && n0 < g.N; n0 += step) ok = launch_backward_tma(plan, pb, n0, g.N - n0 < step ? g.N - n0 : step, st);
+        if (ok) return PWS_OK;
+        plan = nullptr;  // (only fails before anything was launched: attribute setup)
+    }
     for (int n0 = 0; n0 < g.N; n0 += per_chunk) {
         const int nn = (g.N - n0 < per_chunk) ? g.N - n0 : per_chunk;
         if (pb.want_gin) {
@@ -236,7 +245,6 @@ int launch_typed(const Problem &pb, cudaStream_t st)
                                             (size_t)(frame_bytes * nn), st);
             if (e != cudaSuccess) { set_error("backward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return PWS_ECUDA; }
         }
-        if (plan && launch_backward_tma(plan, pb, n0, nn, st)) continue;
         if (lean) { launch_backward_lean(pb, n0, nn, st); continue; }
         const int64_t tiles = (int64_t)tiles_x * tiles_y * nn;
         if (tiles == 0) continue;

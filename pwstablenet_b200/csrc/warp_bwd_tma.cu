@@ -18,6 +18,7 @@
 // bit-identical to the other backward kernels; grad_input differs only by atomic order.
 #include "pws_pipe.cuh"
 
+#include <atomic>
 #include <cstdlib>
 
 namespace pws {
@@ -27,13 +28,34 @@ using namespace pipe;
 namespace {
 
 #ifdef PWS_EXP_NORED   // experiment: drop the scatter's atomics (results are wrong) to time everything else
-#define PWS_RED(p, v) do { if ((v) == 1.2345e-30f) *(p) = (v); } while (0)
+#define PWS_RED(p, v) do { if ((v) == 1.2345e-30f) tma::st_f32_hint((p), (v), pol_last); } while (0)
 #else
-#define PWS_RED(p, v) atomicAdd((p), (v))
+// explicit fire-and-forget reduction: with a fence elsewhere in the kernel nvcc turns atomicAdd into the
+// returning ATOMG form, whose round trip to L2 the scatter would then wait for
+#define PWS_RED(p, v) tma::red_add_f32_hint((p), (v), pol_last)
 #endif
 
+#ifndef PWS_BWD_UNROLL
+#define PWS_BWD_UNROLL 2
+#endif
+constexpr int kRowUnroll = PWS_BWD_UNROLL;
 constexpr int kScouts = 2, kGroups = 2, kGroupWarps = 8, kConsumers = kGroups * kGroupWarps;
-constexpr int kThreads = (1 + kScouts + kConsumers) * 32;
+constexpr int kThreads = (1 + kScouts + kConsumers + 1) * 32;  // + the warp that zero-fills grad_input
+constexpr int kZeroWarp = 1 + kScouts + kConsumers;
+
+// grad_input is zero-filled INSIDE the kernel, one frame at a time, two frames ahead of the scatter: the
+// zeroed lines are still in L2 when the REDs land and no separate memset pass runs ahead of the kernel.
+// A launch owns one slot of per-frame completion counters; the last CTA to leave resets the slot.
+constexpr int kSyncSlots = 64, kSyncFrames = 256;
+__device__ unsigned int g_zero_done[kSyncSlots][kSyncFrames];
+__device__ unsigned int g_exit_count[kSyncSlots];
+
+__device__ __forceinline__ unsigned int ld_relaxed(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 constexpr int kStripRows = 2 * kTH / kGroupWarps;  // a warp owns a 32-column strip of this many rows
 constexpr int kQueueCap = 96;  // entries per consumer warp: 31 left over + 32 lanes x 2 east taps
 
@@ -49,7 +71,8 @@ template <int CS, bool kGgrid> struct Smem {
     static constexpr int kQueueEntry = CS == 3 ? 16 : 8;
     static constexpr int kInfoOff = kQueueOff + kConsumers * kQueueCap * kQueueEntry;
     static constexpr int kBarOff = kInfoOff + kInfoStages * 32;
-    static constexpr int kTotal = kBarOff + (2 * kInStages + 2 * kInfoStages) * 8;
+    static constexpr int kProgressOff = kBarOff + (2 * kInStages + 2 * kInfoStages) * 8;
+    static constexpr int kTotal = kProgressOff + 16;
     static_assert(kInBytes % 128 == 0 && kBoxBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
     static_assert(kInStages % kGroups == 0 && kInfoStages % kGroups == 0, "a stage must always belong to the same consumer group");
@@ -85,7 +108,7 @@ __device__ __forceinline__ void queue_put(Queue<CS> &q, int pos, int off, const 
     else *reinterpret_cast<int2 *>(q.buf + pos) = make_int2(off, __float_as_int(v[0]));
 }
 template <int CS>
-__device__ __forceinline__ void queue_pop_red(const Queue<CS> &q, int pos, float *const (&gipk)[CS])
+__device__ __forceinline__ void queue_pop_red(const Queue<CS> &q, int pos, float *const (&gipk)[CS], const uint64_t pol_last)
 {
     if (CS == 3) {
         const int4 e = *reinterpret_cast<const int4 *>(q.buf + pos);
@@ -99,21 +122,21 @@ __device__ __forceinline__ void queue_pop_red(const Queue<CS> &q, int pos, float
 }
 // dense 32-lane REDs while at least a warp's worth of entries is queued
 template <int CS>
-__device__ __forceinline__ void queue_drain(Queue<CS> &q, float *const (&gipk)[CS], int lane)
+__device__ __forceinline__ void queue_drain(Queue<CS> &q, float *const (&gipk)[CS], int lane, const uint64_t pol_last)
 {
     __syncwarp();
 #pragma unroll 1
     while (q.count >= 32) {
-        queue_pop_red<CS>(q, q.count - 32 + lane, gipk);
+        queue_pop_red<CS>(q, q.count - 32 + lane, gipk, pol_last);
         q.count -= 32;
     }
     __syncwarp();
 }
 template <int CS>
-__device__ __forceinline__ void queue_flush(Queue<CS> &q, float *const (&gipk)[CS], int lane)
+__device__ __forceinline__ void queue_flush(Queue<CS> &q, float *const (&gipk)[CS], int lane, const uint64_t pol_last)
 {
-    queue_drain<CS>(q, gipk, lane);
-    if (lane < q.count) queue_pop_red<CS>(q, lane, gipk);
+    queue_drain<CS>(q, gipk, lane, pol_last);
+    if (lane < q.count) queue_pop_red<CS>(q, lane, gipk, pol_last);
     q.count = 0;
     __syncwarp();
 }
@@ -128,7 +151,7 @@ __device__ __forceinline__ void bwd_row(
     const float *__restrict__ box, const int pitch, const int plane,
     const float *__restrict__ ip, const int sH, const int i_ch, const int H, const int W,
     float *const (&gipk)[CS],
-    float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy, Queue<CS> &q)
+    float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy, Queue<CS> &q, const uint64_t pol_last, const uint64_t pol_first)
 {
     const float dw = fsub(x0f + 1.0f, ix), de = fsub(ix, x0f), dn = fsub(y0f + 1.0f, iy), ds = fsub(iy, y0f);
     unsigned mask = 15u;
@@ -165,8 +188,7 @@ __device__ __forceinline__ void bwd_row(
             if (!kMasked || (mask & 8u)) { gix = ffma(fmul(v3, ds), go[k], gix);  giy = ffma(fmul(v3, de), go[k], giy); }
         }
         gix = fmul(gxm, gix); giy = fmul(gym, giy);
-        if (gg_s3 == 1) *reinterpret_cast<float2 *>(ggq) = make_float2(gix, giy);
-        else { ggq[0] = gix; ggq[gg_s3] = giy; }
+        tma::st_f32_hint(ggq, gix, pol_first); tma::st_f32_hint(ggq + gg_s3, giy, pol_first);
     }
 
     if (kGin) {
@@ -204,7 +226,7 @@ __device__ __forceinline__ void bwd_row(
                 const int n = __popc(b), pos = q.count + __popc(b & lt);
                 if (p_e1) { queue_put<CS>(q, pos, o_nw + 1, etop); queue_put<CS>(q, pos + n, o_nw + W + 1, ebot); }
                 q.count += 2 * n;
-                if (q.count >= 32) queue_drain<CS>(q, gipk, lane);
+                if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
             }
         } else {
             const unsigned b1 = __ballot_sync(0xffffffffu, p_e1), b2 = __ballot_sync(0xffffffffu, p_e2);
@@ -213,7 +235,7 @@ __device__ __forceinline__ void bwd_row(
                 if (p_e1) queue_put<CS>(q, pos1, o_nw + 1, etop);
                 if (p_e2) queue_put<CS>(q, pos2, o_nw + W + 1, ebot);
                 q.count += n1 + __popc(b2);
-                if (q.count >= 32) queue_drain<CS>(q, gipk, lane);
+                if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
             }
         }
         {
@@ -222,7 +244,7 @@ __device__ __forceinline__ void bwd_row(
                 const int pos = q.count + __popc(b & lt);
                 if (p_f) queue_put<CS>(q, pos, o_cy, brk);
                 q.count += __popc(b);
-                if (q.count >= 32) queue_drain<CS>(q, gipk, lane);
+                if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
             }
         }
         cy.x = x0; cy.y = y0 + 1;
@@ -236,7 +258,8 @@ __device__ __forceinline__ void masked_strip(
     const int lane, const int4 info, const int h0, const int w0, const int row0, const int col0,
     const float *__restrict__ mp, const float *__restrict__ gop, const float *__restrict__ bp, const int pitch, const int plane,
     const float *__restrict__ ip, const int sH, const int i_ch, const Geometry g,
-    float *const (&gipk)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Carry<CS> &cy, Queue<CS> &q)
+    float *const (&gipk)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Carry<CS> &cy, Queue<CS> &q,
+    const uint64_t pol_last, const uint64_t pol_first)
 {
     const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
     const bool col_ok = w0 + lane < g.Wo;
@@ -256,10 +279,10 @@ __device__ __forceinline__ void masked_strip(
         const int x0 = (int)x0f, y0 = (int)y0f;
         if (box_taps)
             bwd_row<CS, kGin, kGgrid, true, true>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
-                                                   bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gipk, ggq, gg_s3, cy, q);
+                                                   bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gipk, ggq, gg_s3, cy, q, pol_last, pol_first);
         else
             bwd_row<CS, kGin, kGgrid, true, false>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
-                                                    bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gipk, ggq, gg_s3, cy, q);
+                                                    bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gipk, ggq, gg_s3, cy, q, pol_last, pol_first);
         if (kGgrid) ggq += gg_s1;
     }
 }
@@ -267,7 +290,7 @@ __device__ __forceinline__ void masked_strip(
 template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 __global__ void __launch_bounds__(kThreads, 1)
 bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View gin, const View ggrid, const Geometry g,
-               const int tiles_x, const int tiles_y, const int total_tiles, const int n_begin)
+               const int tiles_x, const int tiles_y, const int total_tiles, const int n_begin, const int n_frames, const int slot, const int zero_ahead)
 {
     using S = Smem<CS, kGgrid>;
     constexpr int kInStages = S::kInStages, kInfoStages = S::kInfoStages;
@@ -280,12 +303,21 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     uint64_t *const in_empty = in_full + kInStages;
     uint64_t *const box_full = in_empty + kInStages;
     uint64_t *const box_empty = box_full + kInfoStages;
+    int *const s_progress = reinterpret_cast<int *>(smem + S::kProgressOff);  // furthest frame any consumer warp of the CTA has reached
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_xy = tiles_x * tiles_y;
     const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
+#ifndef PWS_EXP_POL
+#define PWS_EXP_POL 0
+#endif
+    // experiment knob: 1 = frame boxes with the default policy, 2 = grad_grid stores default, 3 = zero-fill default (REDs evict_last)
+    const uint64_t pol_first = tma::policy_evict_first(), pol_last = tma::policy_evict_last(), pol_norm = tma::policy_evict_normal();
+    const uint64_t pol_box = PWS_EXP_POL == 1 ? pol_norm : pol_first, pol_gg = PWS_EXP_POL == 2 ? pol_norm : pol_first;
+    const uint64_t pol_zero = PWS_EXP_POL == 3 ? pol_norm : pol_last;
 
     if (threadIdx.x == 0) {
+        s_progress[0] = 0;
         for (int s = 0; s < kInStages; ++s) { tma::mbar_init(in_full + s, 1); tma::mbar_init(in_empty + s, kGroupWarps); }
         for (int s = 0; s < kInfoStages; ++s) { tma::mbar_init(box_full + s, 1); tma::mbar_init(box_empty + s, kGroupWarps); }
         tma::fence_barrier_init();
@@ -303,9 +335,9 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
                 float *dst = reinterpret_cast<float *>(s_in + (size_t)s * S::kInBytes);
                 tma::mbar_arrive_expect_tx(in_full + s, S::kInBytes);
-                if (kInter) tma::load_3d(dst, &tp.map, in_full + s, 2 * tc.w0, tc.h0, n_begin + tc.n);
-                else tma::load_4d(dst, &tp.map, in_full + s, tc.w0, tc.h0, 0, n_begin + tc.n);
-                tma::load_4d(dst + kMapTileFloats, &tp.gout, in_full + s, tc.w0, tc.h0, 0, n_begin + tc.n);
+                if (kInter) tma::load_3d_hint(dst, &tp.map, in_full + s, 2 * tc.w0, tc.h0, n_begin + tc.n, pol_first);
+                else tma::load_4d_hint(dst, &tp.map, in_full + s, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
+                tma::load_4d_hint(dst + kMapTileFloats, &tp.gout, in_full + s, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
             }
         }
     } else if (warp <= kScouts) {
@@ -330,10 +362,25 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 else {
                     const int shape = info.z & 0xff;
                     tma::mbar_arrive_expect_tx(box_full + bs, box_w(shape) * box_h(shape) * CS * 4);
-                    tma::load_4d(s_box + (size_t)bs * S::kBoxBytes, &tp.box[shape], box_full + bs, info.x, info.y, 0, n_begin + tc.n);
+                    tma::load_4d_hint(s_box + (size_t)bs * S::kBoxBytes, &tp.box[shape], box_full + bs, info.x, info.y, 0, n_begin + tc.n, pol_box);
                 }
             }
             __syncwarp();
+        }
+    } else if (warp == kZeroWarp) {
+        // ===== zero-fill of grad_input, frame by frame, this CTA's 1/gridDim share, two frames ahead =====
+        if (kGin) {
+            const int64_t frame_vec = (int64_t)gin.sN / 4;  // float4 per frame (host-checked: sN % 4 == 0, base 16-byte aligned)
+            const int64_t share = (frame_vec + gridDim.x - 1) / gridDim.x;
+            const int64_t v0 = (int64_t)blockIdx.x * share, v1 = min(frame_vec, v0 + share);
+            for (int f = 0; f < n_frames; ++f) {
+                while (*reinterpret_cast<volatile int *>(s_progress) + zero_ahead < 8 * f) __nanosleep(256);
+                float4 *__restrict__ dst = reinterpret_cast<float4 *>((float *)gin.p + (int64_t)(n_begin + f) * gin.sN);
+                for (int64_t v = v0 + lane; v < v1; v += 32) tma::st_zero_v4_hint(dst + v, pol_zero);
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(&g_zero_done[slot][f], 1u);
+            }
         }
     } else {
         // ===== consumers: group `grp` owns tiles it = grp, grp + 2, ...; a warp owns a 32 x 8 strip =====
@@ -343,14 +390,29 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
         q.buf = s_queue + cw * kQueueCap;
         q.count = 0;
         const float gxm_in = (kAlign ? Wm1 : Wf) * 0.5f, gym_in = (kAlign ? Hm1 : Hf) * 0.5f;
+        int zero_seen = -1;  // frames [0, zero_seen] are known to be zero-filled by every CTA
         int it = grp;
         for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += kGroups * gridDim.x, it += kGroups) {
             const int is = it % kInStages, iph = (it / kInStages) & 1;
             const int bs = it % kInfoStages, bph = (it / kInfoStages) & 1;
-            tma::mbar_wait(in_full + is, iph);
-            tma::mbar_wait(box_full + bs, bph);
+            // one warp of the group polls the mbarriers, the others park on a hardware barrier (no spin)
+            if (wg == 0) { tma::mbar_wait(in_full + is, iph); tma::mbar_wait(box_full + bs, bph); }
+            tma::named_bar_sync(1 + grp, kGroupWarps * 32);
             const int4 info = s_info[2 * bs], where = s_info[2 * bs + 1];
             const int n = n_begin + info.w, h0 = where.x + row0, w0 = where.y + col0;
+            if (kGin && lane == 0 && wg == 0) {
+                // progress of this CTA in eighths of a frame (the zero-fill warp keeps `zero_ahead` eighths ahead of it)
+                const int in_frame = t - info.w * tiles_xy;
+                atomicMax(s_progress, 8 * info.w + (8 * in_frame) / tiles_xy);
+            }
+            if (kGin && info.w > zero_seen) {
+                if (lane == 0) {  // one lane polls (relaxed), one fence acquires
+                    while (ld_relaxed(&g_zero_done[slot][info.w]) < gridDim.x) __nanosleep(128);
+                    __threadfence();
+                }
+                __syncwarp();
+                zero_seen = info.w;
+            }
             const int shape = info.z & 0xff;
             const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
             const float *mp = reinterpret_cast<const float *>(s_in + (size_t)is * S::kInBytes);
@@ -368,7 +430,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             for (int k = 0; k < CS; ++k) cy.v[k] = 0.f;
 
             if (info.z & kInfoInterior) {
-#pragma unroll 2
+#pragma unroll kRowUnroll
                 for (int r = 0; r < kStripRows; ++r) {
                     float gx, gy, go[CS];
                     if (kInter) { const float2 v = *reinterpret_cast<const float2 *>(mp + (row0 + r) * (2 * kTW) + 2 * (col0 + lane)); gx = v.x; gy = v.y; }
@@ -379,12 +441,12 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                     float x0f, y0f; int x0, y0;
                     floor_small(ix, x0f, x0); floor_small(iy, y0f, y0);
                     bwd_row<CS, kGin, kGgrid, false, true>(lane, true, 0xffffffffu, ix, iy, x0f, y0f, x0, y0, gxm_in, gym_in, go,
-                                                            bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gipk, ggq, ggrid.s3, cy, q);
+                                                            bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gipk, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
                     if (kGgrid) ggq += ggrid.s1;
                 }
             } else {
                 masked_strip<CS, kBorder, kAlign, kInter, kGin, kGgrid>(lane, info, h0, w0, row0, col0, mp, gop, bp, pitch, plane, ip, in.s2, in.s1,
-                                                                        g, gipk, ggq, ggrid.s1, ggrid.s3, cy, q);
+                                                                        g, gipk, ggq, ggrid.s1, ggrid.s3, cy, q, pol_last, pol_gg);
             }
             if (kGin) {
                 if (cy.live) {
@@ -392,17 +454,38 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
 #pragma unroll
                     for (int k = 0; k < CS; ++k) PWS_RED(gipk[k] + o_cy, cy.v[k]);
                 }
-                queue_flush<CS>(q, gipk, lane);
+                queue_flush<CS>(q, gipk, lane, pol_last);
             }
             __syncwarp();
             if (lane == 0) { tma::mbar_arrive(in_empty + is); tma::mbar_arrive(box_empty + bs); }
         }
+        if (kGin && lane == 0) atomicMax(s_progress, INT_MAX - 4);  // out of tiles: let the zero-fill warp run to the end
     }
+    if (kGin) {
+        // the last CTA to leave hands the counter slot back clean
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&g_exit_count[slot], 1u) == gridDim.x - 1) {
+                for (int f = 0; f < n_frames; ++f) g_zero_done[slot][f] = 0u;
+                g_exit_count[slot] = 0u;
+                __threadfence();
+            }
+        }
+    }
+}
+
+int zero_ahead()
+{
+    // how far the zero-fill runs ahead of the scatter, in eighths of a frame
+    static const int v = [] { const char *e = std::getenv("PWS_BWD_ZERO_AHEAD"); int a = e ? std::atoi(e) : 4; return a < 1 ? 1 : a; }();
+    return v;
 }
 
 template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, int total, int n0, cudaStream_t st)
 {
+    static std::atomic<unsigned> next_slot{0};
     auto kern = bwd_tma_kernel<CS, kBorder, kAlign, kInter, kGin, kGgrid>;
     using S = Smem<CS, kGgrid>;
     static bool attr_done = false;  // per instantiation
@@ -414,7 +497,9 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
         attr_done = true;
     }
     const int grid = total < sm_count() ? total : sm_count();
-    kern<<<grid, kThreads, S::kTotal, st>>>(tp, pb.in, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0);
+    const int n_frames = total / (tiles_x * tiles_y);
+    const int slot = (int)(next_slot.fetch_add(1u, std::memory_order_relaxed) % kSyncSlots);
+    kern<<<grid, kThreads, S::kTotal, st>>>(tp, pb.in, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0, n_frames, slot, zero_ahead());
     note_launch();
     return true;
 }
@@ -455,6 +540,8 @@ BwdTmaPlan *backward_tma_plan(const Problem &pb)
     if (g.C != 1 && g.C != 3) return nullptr;
     if (g.W > (1 << 22) || g.H > (1 << 22)) return nullptr;
     if (pb.want_gin && !(pb.gin.s3 == 1 && pb.gin.s2 == g.W && pb.gin.s1 == g.W * g.H)) return nullptr;
+    // in-kernel zero-fill writes float4: frame base and frame stride 16-byte aligned
+    if (pb.want_gin && ((reinterpret_cast<uintptr_t>(pb.gin.p) & 15) || (pb.gin.sN % 4))) return nullptr;
     if (pb.want_ggrid) {
         // written with plain stores: planar (two scalars) or interleaved (one float2)
         if (pb.ggrid.s3 == 1 && ((reinterpret_cast<uintptr_t>(pb.ggrid.p) & 7) || (pb.ggrid.sN & 1) || (pb.ggrid.s1 & 1) || (pb.ggrid.s2 & 1)))
@@ -473,7 +560,9 @@ BwdTmaPlan *backward_tma_plan(const Problem &pb)
 
 void backward_tma_free(BwdTmaPlan *pl) { delete pl; }
 
-// Launch frames [n0, n0+nn).
+int backward_tma_max_frames() { return kSyncFrames; }
+
+// Launch frames [n0, n0+nn), nn <= backward_tma_max_frames().  Zero-fills grad_input of those frames itself.
 bool launch_backward_tma(const BwdTmaPlan *pl, const Problem &pb, int n0, int nn, cudaStream_t st)
 {
     const int total = pl->tiles_x * pl->tiles_y * nn;

@@ -120,8 +120,9 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
         for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += kGroups * gridDim.x, it += kGroups) {
             const int ms = it % kMapStages, mph = (it / kMapStages) & 1;
             const int bs = it % kBoxStages, bph = (it / kBoxStages) & 1;
-            tma::mbar_wait(map_full + ms, mph);
-            tma::mbar_wait(box_full + bs, bph);
+            // one warp of the group polls the mbarriers, the others park on a hardware barrier (no spin)
+            if (wg == 0) { tma::mbar_wait(map_full + ms, mph); tma::mbar_wait(box_full + bs, bph); }
+            tma::named_bar_sync(1 + grp, kGroupWarps * 32);
             const float *mp = s_map + ms * kMapTileFloats;
             const int4 info = s_info[2 * bs], where = s_info[2 * bs + 1];
             TileCoord tc;

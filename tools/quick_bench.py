@@ -29,6 +29,7 @@ def timeit(fn, iters=10, warm=3):
 
 def main():
     cases = [("1080p", 16, 3, 1080, 1920), ("720p", 32, 3, 720, 1280), ("256", 16, 3, 256, 256)]
+    if os.environ.get("QB_ONLY_1080"): cases = cases[:1]
     kinds = sys.argv[1].split(",") if len(sys.argv) > 1 else ["smooth", "random", "centre"]
     print(torch.cuda.get_device_name(0), "chunkMB", os.environ.get("PWS_BWD_CHUNK_MB", "32"))
     for name, N, C, H, W in cases:
@@ -43,7 +44,7 @@ def main():
             fb, bb = 32 * px, 52 * px
             for gname, gr in (("interleaved", grid), ("planar", planar)):
                 res = {}
-                for impl, fwd in (("ours", pw.warp2d_forward), ("torch", None)):
+                for impl, fwd in ((("ours", pw.warp2d_forward),) if os.environ.get("QB_NO_TORCH") else (("ours", pw.warp2d_forward), ("torch", None))):
                     if impl == "ours":
                         f = lambda: pw.warp2d_forward(frames, gr, 0, False)
                         b = lambda: pw.warp2d_backward(gout, frames, gr, 0, False, (True, True))
