@@ -308,13 +308,12 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_xy = tiles_x * tiles_y;
     const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
-#ifndef PWS_EXP_POL
-#define PWS_EXP_POL 0
-#endif
-    // experiment knob: 1 = frame boxes with the default policy, 2 = grad_grid stores default, 3 = zero-fill default (REDs evict_last)
-    const uint64_t pol_first = tma::policy_evict_first(), pol_last = tma::policy_evict_last(), pol_norm = tma::policy_evict_normal();
-    const uint64_t pol_box = PWS_EXP_POL == 1 ? pol_norm : pol_first, pol_gg = PWS_EXP_POL == 2 ? pol_norm : pol_first;
-    const uint64_t pol_zero = PWS_EXP_POL == 3 ? pol_norm : pol_last;
+    // L2 priorities: everything that streams through once (map, grad_output, frame boxes, grad_grid) is evict_first,
+    // so the replacement order favours grad_input, which is revisited between its zero-fill and its last RED.
+    // (evict_last for grad_input was tried: its lines then outlive the kernel and crowd the next one out of L2.)
+    const uint64_t pol_first = tma::policy_evict_first();
+    const uint64_t pol_last = tma::policy_evict_normal();
+    const uint64_t pol_box = pol_first, pol_gg = pol_first, pol_zero = pol_last;
 
     if (threadIdx.x == 0) {
         s_progress[0] = 0;
@@ -395,24 +394,28 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
         for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += kGroups * gridDim.x, it += kGroups) {
             const int is = it % kInStages, iph = (it / kInStages) & 1;
             const int bs = it % kInfoStages, bph = (it / kInfoStages) & 1;
-            // one warp of the group polls the mbarriers, the others park on a hardware barrier (no spin)
-            if (wg == 0) { tma::mbar_wait(in_full + is, iph); tma::mbar_wait(box_full + bs, bph); }
+            // one warp of the group polls (the mbarriers and, on a new frame, the zero-fill counter of that frame);
+            // the others park on a hardware barrier and spin on nothing
+            if (wg == 0) {
+                tma::mbar_wait(in_full + is, iph);
+                tma::mbar_wait(box_full + bs, bph);
+                if (kGin) {
+                    const int f = s_info[2 * bs].w;
+                    if (lane == 0) {
+                        // progress of this CTA in eighths of a frame (the zero-fill warp keeps `zero_ahead` eighths ahead of it)
+                        atomicMax(s_progress, 8 * f + (8 * (t - f * tiles_xy)) / tiles_xy);
+                        if (f > zero_seen) {
+                            while (ld_relaxed(&g_zero_done[slot][f]) < gridDim.x) __nanosleep(64);
+                            __threadfence();
+                        }
+                    }
+                    zero_seen = f;
+                    __syncwarp();
+                }
+            }
             tma::named_bar_sync(1 + grp, kGroupWarps * 32);
             const int4 info = s_info[2 * bs], where = s_info[2 * bs + 1];
             const int n = n_begin + info.w, h0 = where.x + row0, w0 = where.y + col0;
-            if (kGin && lane == 0 && wg == 0) {
-                // progress of this CTA in eighths of a frame (the zero-fill warp keeps `zero_ahead` eighths ahead of it)
-                const int in_frame = t - info.w * tiles_xy;
-                atomicMax(s_progress, 8 * info.w + (8 * in_frame) / tiles_xy);
-            }
-            if (kGin && info.w > zero_seen) {
-                if (lane == 0) {  // one lane polls (relaxed), one fence acquires
-                    while (ld_relaxed(&g_zero_done[slot][info.w]) < gridDim.x) __nanosleep(128);
-                    __threadfence();
-                }
-                __syncwarp();
-                zero_seen = info.w;
-            }
             const int shape = info.z & 0xff;
             const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
             const float *mp = reinterpret_cast<const float *>(s_in + (size_t)is * S::kInBytes);
@@ -462,8 +465,8 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
         if (kGin && lane == 0) atomicMax(s_progress, INT_MAX - 4);  // out of tiles: let the zero-fill warp run to the end
     }
     if (kGin) {
-        // the last CTA to leave hands the counter slot back clean
         __syncthreads();
+        // the last CTA to leave hands the counter slot back clean
         if (threadIdx.x == 0) {
             __threadfence();
             if (atomicAdd(&g_exit_count[slot], 1u) == gridDim.x - 1) {
