@@ -12,8 +12,9 @@ FRAMES 1080p fp32 RGB frames per GPU, through the C ABI of libpwswarp.so.
   e2e          same metric through the user-facing call (pwstablenet_b200.grid_sample
                pipeline) with PINNED HOST buffers: H2D of frames/map/grad_output and
                D2H of output/grad_frame/grad_map inside the timed region
-  roofline     backward kernel (the dominant one): algorithmic bytes (52 B/pixel)
-               / CUDA-event time of the backward call, against MEASURED_PEAKS.json
+  roofline     backward kernel (bwd_tma_kernel, the dominant one: 71 % of the step live, 72 % in the ncu launch
+               list profiles/r01_launches_bench.csv): algorithmic bytes (52 B/pixel) / CUDA-event time
+               of the backward call, against MEASURED_PEAKS.json; `traffic` = DRAM bytes of the same launch from ncu
   cpu_baseline the reference's own CPU path -- torch.nn.functional.grid_sample on CPU
                tensors exactly as R/main_new.py:106,116,716 call it -- timed on this box's
                host cores over a bounded sample
@@ -43,6 +44,7 @@ import torch
 H, W, C = 1080, 1920, 3
 FRAMES = 16                      # frames per GPU per step
 FWD_BYTES_PX, BWD_BYTES_PX = 32, 52   # algorithmic bytes per output pixel, fp32 C=3
+NCU_BWD_DRAM_BYTES = 1_185_143_000 + 699_599_000   # ncu --set full, 16-frame backward launch: read + write (profiles/r01_bwd_tma.txt)
 WORKLOAD = ("1080p (1920x1080) fp32 RGB bilinear warp, forward + backward (grad to frame and map), "
             f"{FRAMES} frames/GPU/step, zeros padding, align_corners=False, NCHW frames, planar-stored map "
             "= identity + 0.03*tanh(low-pass noise)")
@@ -309,7 +311,9 @@ def main():
                     "api": "pwstablenet_b200.HostWarpPipeline.run(): pinned host buffers in and out, 2-frame chunks, H2D / fwd+bwd through the C ABI / D2H overlapped on 3 streams"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "bwd_tma_kernel (pws_warp2d_backward)", "achieved": bwd_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": bwd_gbs / peak, "peak_source": peak_src, "traffic": None,
+                         "unit": "GB/s", "frac": bwd_gbs / peak, "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one 16-frame launch (profiles/r01_bwd_tma.txt)
+                         "traffic": NCU_BWD_DRAM_BYTES if FRAMES == 16 else None,
                          "algorithmic_bytes_per_launch_set": BWD_BYTES_PX * px, "ms": bwd_ms,
                          "frac_of_8TBs_nominal": bwd_gbs / 8000.0,
                          "forward": {"achieved": fwd_gbs, "frac": fwd_gbs / peak, "ms": fwd_ms},
