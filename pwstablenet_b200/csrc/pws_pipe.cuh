@@ -62,6 +62,25 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_x, int tiles_xy
     return c;
 }
 
+// Walks tiles t0, t0 + step, t0 + 2*step, ... without a division per tile.
+struct TileWalk {
+    int n, ty, tx;        // current tile
+    int dn, dy, dx;       // decomposition of `step`
+    __device__ __forceinline__ void init(int t0, int step, int tiles_x, int tiles_y)
+    {
+        const int tiles_xy = tiles_x * tiles_y;
+        n = t0 / tiles_xy; int r = t0 - n * tiles_xy; ty = r / tiles_x; tx = r - ty * tiles_x;
+        dn = step / tiles_xy; r = step - dn * tiles_xy; dy = r / tiles_x; dx = r - dy * tiles_x;
+    }
+    __device__ __forceinline__ void next(int tiles_x, int tiles_y)
+    {
+        tx += dx; if (tx >= tiles_x) { tx -= tiles_x; ty += 1; }
+        ty += dy; if (ty >= tiles_y) { ty -= tiles_y; n += 1; }
+        n += dn;
+    }
+    __device__ __forceinline__ TileCoord coord() const { TileCoord c; c.n = n; c.h0 = ty * kTH; c.w0 = tx * kTW; return c; }
+};
+
 // Extremes of the x and y map values of a tile, over its valid rows x cols, NaN-propagating.
 // Planar tile: [2][kTH][kTW]; interleaved: [kTH][kTW][2].  All 32 lanes of a warp call this.
 template <bool kInter>
@@ -114,13 +133,11 @@ __device__ __forceinline__ void map_tile_range(const float *__restrict__ mp, int
                 ylo = fmin_nan(ylo, fmin4(vy)); yhi = fmax_nan(yhi, fmax4(vy));
             }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        xlo = fmin_nan(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
-        xhi = fmax_nan(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
-        ylo = fmin_nan(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
-        yhi = fmax_nan(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
-    }
+    // one warp-wide reduction instruction per extreme (sm_100a: redux.sync on f32 -> CREDUX)
+    asm volatile("redux.sync.min.NaN.f32 %0, %1, 0xffffffff;" : "=f"(xlo) : "f"(xlo));
+    asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(xhi) : "f"(xhi));
+    asm volatile("redux.sync.min.NaN.f32 %0, %1, 0xffffffff;" : "=f"(ylo) : "f"(ylo));
+    asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(yhi) : "f"(yhi));
 }
 
 // From the extremes of a tile's map to the box of the frame its taps need: (bx, by, shape | flags).

@@ -305,7 +305,9 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     uint64_t *const box_empty = box_full + kInfoStages;
     int *const s_progress = reinterpret_cast<int *>(smem + S::kProgressOff);  // furthest frame any consumer warp of the CTA has reached
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Roles are numbered from the TOP warp of the CTA down (the scheduler favours the higher warp ids when several
+    // warps are ready; the producer and the scouts are a handful of instructions per tile, but every consumer waits on them).
+    const int warp = (kThreads / 32 - 1) - (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int tiles_xy = tiles_x * tiles_y;
     const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
     // L2 priorities: everything that streams through once (map, grad_output, frame boxes, grad_grid) is evict_first,
@@ -328,10 +330,12 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
         if (lane == 0) {
             tma::prefetch_desc(&tp.map); tma::prefetch_desc(&tp.gout);
             int it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            TileWalk tw;
+            tw.init(blockIdx.x, gridDim.x, tiles_x, tiles_y);
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it, tw.next(tiles_x, tiles_y)) {
                 const int s = it % kInStages, ph = (it / kInStages) & 1;
                 tma::mbar_wait_relaxed(in_empty + s, ph ^ 1);
-                const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
+                const TileCoord tc = tw.coord();
                 float *dst = reinterpret_cast<float *>(s_in + (size_t)s * S::kInBytes);
                 tma::mbar_arrive_expect_tx(in_full + s, S::kInBytes);
                 if (kInter) tma::load_3d_hint(dst, &tp.map, in_full + s, 2 * tc.w0, tc.h0, n_begin + tc.n, pol_first);
@@ -343,10 +347,12 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
         // ===== scouts (alternate tiles): map tile -> tap bounding box -> frame box load =====
         if (kGgrid && lane == 0) { tma::prefetch_desc(&tp.box[0]); tma::prefetch_desc(&tp.box[1]); tma::prefetch_desc(&tp.box[2]); }
         int it = warp - 1;
-        for (int t = blockIdx.x + (warp - 1) * gridDim.x; t < total_tiles; t += kScouts * gridDim.x, it += kScouts) {
+        TileWalk tw;
+        tw.init(blockIdx.x + (warp - 1) * gridDim.x, kScouts * gridDim.x, tiles_x, tiles_y);
+        for (int t = blockIdx.x + (warp - 1) * gridDim.x; t < total_tiles; t += kScouts * gridDim.x, it += kScouts, tw.next(tiles_x, tiles_y)) {
             const int is = it % kInStages, iph = (it / kInStages) & 1;
             const int bs = it % kInfoStages, bph = (it / kInfoStages) & 1;
-            const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
+            const TileCoord tc = tw.coord();
             const int cols = min(kTW, g.Wo - tc.w0), rows = min(kTH, g.Ho - tc.h0);
             tma::mbar_wait_relaxed(in_full + is, iph);
             float xlo, xhi, ylo, yhi;
