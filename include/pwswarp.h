@@ -80,6 +80,10 @@ const char *pws_last_error(void);
  * bench.py reports the difference over its timed region as "gpu_launches". */
 uint64_t pws_launch_count(void);
 
+/* Debug / tests: name of the kernel family the last forward / backward call on THIS thread launched
+ * ("fwd_tma", "fwd_lean", "fwd_direct", "bwd_tma", "bwd_lean", "bwd_march", "fused", ...; "" before any call). */
+const char *pws_last_kernel(void);
+
 /* out[n,c,h,w] = sum over the 4 bilinear taps of in[n,c,y_tap,x_tap] * w_tap,
  * replaces aten::grid_sampler_2d for interp = bilinear, padding in {zeros, border}.
  * Frame dtype: f32, f16, bf16, f64.  Map dtype: the frame's dtype or f32 (an

@@ -16,6 +16,7 @@ EXPORTS = (
     "pws_abi_version",
     "pws_last_error",
     "pws_launch_count",
+    "pws_last_kernel",
     "pws_warp2d_forward",
     "pws_warp2d_backward",
     "pws_warp2d_taps",
@@ -72,6 +73,7 @@ def load() -> ctypes.CDLL:
     lib.pws_abi_version.restype = ctypes.c_int
     lib.pws_last_error.restype = ctypes.c_char_p
     lib.pws_launch_count.restype = ctypes.c_uint64
+    lib.pws_last_kernel.restype = ctypes.c_char_p
     lib.pws_warp2d_forward.restype = ctypes.c_int
     lib.pws_warp2d_forward.argtypes = [P, P, P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.pws_warp2d_backward.restype = ctypes.c_int
@@ -94,6 +96,11 @@ def load() -> ctypes.CDLL:
 def launch_count() -> int:
     """Kernels launched by libpwswarp.so so far in this process."""
     return int(load().pws_launch_count())
+
+
+def last_kernel() -> str:
+    """Kernel family the last forward / backward call on this thread launched (debug / tests)."""
+    return load().pws_last_kernel().decode("ascii", "replace")
 
 
 def last_error() -> str:

@@ -13,7 +13,9 @@ namespace pws {
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 
+static thread_local const char *g_last_kernel = "";
 void note_launch(int kernels) { g_launches.fetch_add((uint64_t)kernels, std::memory_order_relaxed); }
+void note_kernel(const char *family) { g_last_kernel = family; }
 
 void set_error(const char *fmt, ...)
 {
@@ -202,6 +204,8 @@ __attribute__((visibility("default"))) int pws_abi_version(void) { return PWS_AB
 __attribute__((visibility("default"))) const char *pws_last_error(void) { return g_err; }
 
 __attribute__((visibility("default"))) uint64_t pws_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+__attribute__((visibility("default"))) const char *pws_last_kernel(void) { return g_last_kernel; }
 
 __attribute__((visibility("default")))
 int pws_warp2d_forward(const pws_tensor *in, const pws_tensor *grid, pws_tensor *out,

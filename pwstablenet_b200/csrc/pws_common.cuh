@@ -131,6 +131,7 @@ __device__ __forceinline__ void make_taps(A ix, A iy, int H, int W, Taps<A> &t)
 // ---- error plumbing (host) -----------------------------------------------------------
 void set_error(const char *fmt, ...);
 void note_launch(int kernels = 1);  // bumps the counter pws_launch_count() reports
+void note_kernel(const char *family);  // what pws_last_kernel() reports (thread-local)
 
 struct Problem {  // validated, kernel-ready description of one call
     Geometry g;

@@ -245,6 +245,7 @@ int launch_typed(const Problem &pb, cudaStream_t st)
                                             (size_t)(frame_bytes * nn), st);
             if (e != cudaSuccess) { set_error("backward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return PWS_ECUDA; }
         }
+        note_kernel(lean ? "bwd_lean" : "bwd_march");
         if (lean) { launch_backward_lean(pb, n0, nn, st); continue; }
         const int64_t tiles = (int64_t)tiles_x * tiles_y * nn;
         if (tiles == 0) continue;

@@ -510,6 +510,7 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
     const int slot = (int)(next_slot.fetch_add(1u, std::memory_order_relaxed) % kSyncSlots);
     kern<<<grid, kThreads, S::kTotal, st>>>(tp, pb.in, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0, n_frames, slot, zero_ahead());
     note_launch();
+    note_kernel("bwd_tma");
     return true;
 }
 

@@ -149,7 +149,8 @@ int launch_forward(const Problem &pb, cudaStream_t st)
     if (!force_direct() && batch_mode() < 0 && launch_forward_march(pb, st)) return PWS_OK;
     if (!force_direct() && batch_mode() > 0 && launch_forward_batch(pb, batch_mode(), st)) return PWS_OK;
     if (!force_direct() && launch_forward_tma(pb, st)) return PWS_OK;
-    if (!force_direct() && launch_forward_tile(pb, st)) return PWS_OK;
+    if (!force_direct() && launch_forward_tile(pb, st)) { note_kernel("fwd_lean"); return PWS_OK; }
+    note_kernel("fwd_direct");
     const int it = pb.in_dtype, gt = pb.grid_dtype;
     if (it == PWS_F32 && gt == PWS_F32) return launch_direct<float, float>(pb, st);
     if (it == PWS_F64 && gt == PWS_F64) return launch_direct<double, double>(pb, st);

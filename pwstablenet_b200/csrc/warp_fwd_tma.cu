@@ -239,6 +239,7 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
     const int grid = total < sm_count() ? total : sm_count();
     kern<<<grid, kThreads, Smem<CS>::kTotal, st>>>(tp, pb.in, pb.out, pb.g, tiles_x, tiles_y, total);
     note_launch();
+    note_kernel("fwd_tma");
     return true;
 }
 
