@@ -19,6 +19,9 @@ constexpr int kBW0 = 72, kBH0 = 20, kBW1 = 80, kBH1 = 24, kBW2 = 88, kBH2 = 28; 
 constexpr int kMaxBW = kBW2, kMaxBH = kBH2;
 __host__ __device__ constexpr int box_w(int s) { return s == 0 ? kBW0 : s == 1 ? kBW1 : kBW2; }
 __host__ __device__ constexpr int box_h(int s) { return s == 0 ? kBH0 : s == 1 ? kBH1 : kBH2; }
+// channels-last RGB frames: the box is (3 * width) elements wide and a TMA box dimension holds at most 256
+constexpr int kBW2CL = 84;
+template <bool kCL> __host__ __device__ constexpr int box_w_of(int s) { return kCL && s == 2 ? kBW2CL : box_w(s); }
 
 // info.z of a tile: box shape in the low byte plus
 enum : int {
@@ -140,9 +143,88 @@ __device__ __forceinline__ void map_tile_range(const float *__restrict__ mp, int
     asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(yhi) : "f"(yhi));
 }
 
+// The same extremes read straight from global memory, in two halves so that a scout can keep the loads of its NEXT
+// tile in flight while it deals with the current one (a global load takes ~3 us under this kernel's traffic; the
+// scout would otherwise spend most of a tile time waiting for it).
+// `tp` points at the tile's first x coordinate; s1 = row stride, s3 = stride between the x and y coordinates
+// (planar maps) -- interleaved maps hold (x,y) pairs.  Alignment is the TMA eligibility of encode_map_tma.
+// volatile: the load must be ISSUED where it is written (the compiler otherwise sinks it to its first use to save
+// registers, which puts the whole memory latency back on the scout's path)
+__device__ __forceinline__ float4 ldg_v4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+struct MapRegs { float4 v[kTH]; };
+// loads of a FULL tile (kTH rows x kTW columns): 16 independent 128-bit loads per lane
+template <bool kInter>
+__device__ __forceinline__ void map_tile_fetch(const float *__restrict__ tp, int s1, int s3, int lane, MapRegs &m)
+{
+    if (kInter) {
+#pragma unroll
+        for (int k = 0; k < kTH; ++k) m.v[k] = ldg_v4(tp + k * s1 + 4 * lane);  // a row is 128 floats: one per lane and row
+    } else {
+        const int c4 = (lane & 15) * 4, rr = lane >> 4;  // 16 lanes per row of 64, two rows per instruction
+#pragma unroll
+        for (int k = 0; k < kTH / 2; ++k) { m.v[k] = ldg_v4(tp + (2 * k + rr) * s1 + c4); m.v[kTH / 2 + k] = ldg_v4(tp + s3 + (2 * k + rr) * s1 + c4); }
+    }
+}
+__device__ __forceinline__ void warp_range(float &xlo, float &xhi, float &ylo, float &yhi)
+{
+    // one warp-wide reduction instruction per extreme (sm_100a: redux.sync on f32 -> CREDUX)
+    asm volatile("redux.sync.min.NaN.f32 %0, %1, 0xffffffff;" : "=f"(xlo) : "f"(xlo));
+    asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(xhi) : "f"(xhi));
+    asm volatile("redux.sync.min.NaN.f32 %0, %1, 0xffffffff;" : "=f"(ylo) : "f"(ylo));
+    asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(yhi) : "f"(yhi));
+}
+template <bool kInter>
+__device__ __forceinline__ void map_tile_reduce(const MapRegs &m, float &xlo, float &xhi, float &ylo, float &yhi)
+{
+    xlo = INFINITY; xhi = -INFINITY; ylo = INFINITY; yhi = -INFINITY;
+    if (kInter) {
+#pragma unroll
+        for (int k = 0; k < kTH; ++k) {
+            xlo = fmin3_nan(xlo, m.v[k].x, m.v[k].z); xhi = fmax3_nan(xhi, m.v[k].x, m.v[k].z);
+            ylo = fmin3_nan(ylo, m.v[k].y, m.v[k].w); yhi = fmax3_nan(yhi, m.v[k].y, m.v[k].w);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kTH / 2; ++k) {
+            xlo = fmin_nan(xlo, fmin4(m.v[k])); xhi = fmax_nan(xhi, fmax4(m.v[k]));
+            ylo = fmin_nan(ylo, fmin4(m.v[kTH / 2 + k])); yhi = fmax_nan(yhi, fmax4(m.v[kTH / 2 + k]));
+        }
+    }
+    warp_range(xlo, xhi, ylo, yhi);
+}
+// partial tiles (the last tile row / column of a frame): load and reduce in one go
+template <bool kInter>
+__device__ __forceinline__ void map_tile_range_global(const float *__restrict__ tp, int s1, int s3, int rows, int cols, int lane,
+                                                      float &xlo, float &xhi, float &ylo, float &yhi)
+{
+    xlo = INFINITY; xhi = -INFINITY; ylo = INFINITY; yhi = -INFINITY;
+    if (kInter) {
+        if (2 * lane < cols)  // a lane covers 2 pixels of every row (cols is a multiple of 4)
+            for (int r = 0; r < rows; ++r) {
+                const float4 v = ldg_v4(tp + r * s1 + 4 * lane);
+                xlo = fmin3_nan(xlo, v.x, v.z); xhi = fmax3_nan(xhi, v.x, v.z);
+                ylo = fmin3_nan(ylo, v.y, v.w); yhi = fmax3_nan(yhi, v.y, v.w);
+            }
+    } else {
+        const int c4 = (lane & 15) * 4;
+        if (c4 < cols)
+            for (int r = lane >> 4; r < rows; r += 2) {
+                const float4 vx = ldg_v4(tp + r * s1 + c4), vy = ldg_v4(tp + s3 + r * s1 + c4);
+                xlo = fmin_nan(xlo, fmin4(vx)); xhi = fmax_nan(xhi, fmax4(vx));
+                ylo = fmin_nan(ylo, fmin4(vy)); yhi = fmax_nan(yhi, fmax4(vy));
+            }
+    }
+    warp_range(xlo, xhi, ylo, yhi);
+}
+
 // From the extremes of a tile's map to the box of the frame its taps need: (bx, by, shape | flags).
 // unnormalise is monotone, so the extremes of the map give the extremes of the taps.
-template <bool kBorder, bool kAlign>
+template <bool kBorder, bool kAlign, bool kCL = false>
 __device__ __forceinline__ int4 box_of_range(float xlo, float xhi, float ylo, float yhi, int W, int H, bool full_tile)
 {
     const float Wf = (float)W, Hf = (float)H, Wm1 = (float)(W - 1), Hm1 = (float)(H - 1);
@@ -165,7 +247,7 @@ __device__ __forceinline__ int4 box_of_range(float xlo, float xhi, float ylo, fl
     const int bx = max(x0lo, 0) & ~3, by = max(y0lo, 0);
     const int bw = min(x0hi + 1, W - 1) - bx + 1, bh = min(y0hi + 1, H - 1) - by + 1;
     if (bw <= 0 || bh <= 0) return make_int4(0, 0, kInfoEmpty, 0);
-    const int shape = bw <= kBW0 && bh <= kBH0 ? 0 : bw <= kBW1 && bh <= kBH1 ? 1 : bw <= kBW2 && bh <= kBH2 ? 2 : -1;
+    const int shape = bw <= kBW0 && bh <= kBH0 ? 0 : bw <= kBW1 && bh <= kBH1 ? 1 : bw <= box_w_of<kCL>(2) && bh <= kBH2 ? 2 : -1;
     if (shape < 0) return make_int4(0, 0, kInfoFallback, 0);
     return make_int4(bx, by, shape | (interior ? kInfoInterior : 0), 0);
 }

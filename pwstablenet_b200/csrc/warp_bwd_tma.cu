@@ -19,6 +19,7 @@
 #include "pws_pipe.cuh"
 
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 
 namespace pws {
@@ -40,8 +41,10 @@ namespace {
 #endif
 constexpr int kRowUnroll = PWS_BWD_UNROLL;
 constexpr int kScouts = 2, kGroups = 2, kGroupWarps = 8, kConsumers = kGroups * kGroupWarps;
-constexpr int kThreads = (1 + kScouts + kConsumers + 1) * 32;  // + the warp that zero-fills grad_input
-constexpr int kZeroWarp = 1 + kScouts + kConsumers;
+constexpr int kThreads = (kScouts + kConsumers + 1) * 32;  // scouts, consumers, the warp that zero-fills grad_input
+constexpr int kZeroWarp = kScouts + kConsumers;
+static_assert(kScouts == kGroups, "scout w feeds consumer group w (and tells it when the tiles have run out)");
+constexpr int kInfoStop = 1 << 11;  // info.z: no more tiles for this consumer group
 
 // grad_input is zero-filled INSIDE the kernel, one frame at a time, two frames ahead of the scatter: the
 // zeroed lines are still in L2 when the REDs land and no separate memset pass runs ahead of the kernel.
@@ -49,33 +52,45 @@ constexpr int kZeroWarp = 1 + kScouts + kConsumers;
 constexpr int kSyncSlots = 64, kSyncFrames = 256;
 __device__ unsigned int g_zero_done[kSyncSlots][kSyncFrames];
 __device__ unsigned int g_exit_count[kSyncSlots];
+// Tiles are handed out dynamically: the SMs of a B200 do not run this kernel at the same pace (the spread is several
+// per cent: distance to the L2 slices, neighbours on the same TPC), and with a static round-robin every frame ended
+// with the fast CTAs waiting at the zero-fill counter of the next frame for the slow ones.
+__device__ unsigned int g_tile_next[kSyncSlots];
 
-__device__ __forceinline__ unsigned int ld_relaxed(const unsigned int *p)
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
 {
     unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 constexpr int kStripRows = 2 * kTH / kGroupWarps;  // a warp owns a 32-column strip of this many rows
 constexpr int kQueueCap = 96;  // entries per consumer warp: 31 left over + 32 lanes x 2 east taps
 
+// ring depth and the largest box shape a ring slot holds (tiles that need a larger box gather from global memory)
+#ifndef PWS_BWD_STAGES
+#define PWS_BWD_STAGES 4
+#endif
+#ifndef PWS_BWD_SLOT_SHAPE
+#define PWS_BWD_SLOT_SHAPE 2
+#endif
+constexpr int kSlotShape = PWS_BWD_SLOT_SHAPE;
+
+// One ring: a stage holds everything a tile needs -- its map + grad_output tile, its frame box, its info words --
+// behind one `full` and one `empty` mbarrier.
 template <int CS, bool kGgrid> struct Smem {
-    static constexpr int kInStages = kGgrid ? 4 : 6;
-    static constexpr int kInfoStages = 4;
-    static constexpr int kBoxStages = kGgrid ? kInfoStages : 0;
+    static constexpr int kStages = kGgrid ? PWS_BWD_STAGES : 6;
     static constexpr int kInBytes = kMapTileBytes + CS * kTW * kTH * 4;
-    static constexpr int kBoxBytes = kMaxBW * kMaxBH * CS * 4;
+    static constexpr int kBoxBytes = kGgrid ? box_w(kSlotShape) * box_h(kSlotShape) * CS * 4 : 0;
     static constexpr int kInOff = 0;
-    static constexpr int kBoxOff = kInStages * kInBytes;
-    static constexpr int kQueueOff = kBoxOff + kBoxStages * kBoxBytes;
+    static constexpr int kBoxOff = kStages * kInBytes;
+    static constexpr int kQueueOff = kBoxOff + kStages * kBoxBytes;
     static constexpr int kQueueEntry = CS == 3 ? 16 : 8;
     static constexpr int kInfoOff = kQueueOff + kConsumers * kQueueCap * kQueueEntry;
-    static constexpr int kBarOff = kInfoOff + kInfoStages * 32;
-    static constexpr int kProgressOff = kBarOff + (2 * kInStages + 2 * kInfoStages) * 8;
+    static constexpr int kBarOff = kInfoOff + kStages * 32;
+    static constexpr int kProgressOff = kBarOff + 2 * kStages * 8;
     static constexpr int kTotal = kProgressOff + 16;
     static_assert(kInBytes % 128 == 0 && kBoxBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
-    static_assert(kInStages % kGroups == 0 && kInfoStages % kGroups == 0, "a stage must always belong to the same consumer group");
 };
 
 struct TmaParams {
@@ -289,24 +304,22 @@ __device__ __forceinline__ void masked_strip(
 
 template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 __global__ void __launch_bounds__(kThreads, 1)
-bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View gin, const View ggrid, const Geometry g,
+bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View grid, const View gin, const View ggrid, const Geometry g,
                const int tiles_x, const int tiles_y, const int total_tiles, const int n_begin, const int n_frames, const int slot, const int zero_ahead)
 {
     using S = Smem<CS, kGgrid>;
-    constexpr int kInStages = S::kInStages, kInfoStages = S::kInfoStages;
+    constexpr int kStages = S::kStages;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *const s_in = smem + S::kInOff;
     unsigned char *const s_box = smem + S::kBoxOff;
     QEntry<CS> *const s_queue = reinterpret_cast<QEntry<CS> *>(smem + S::kQueueOff);
     int4 *const s_info = reinterpret_cast<int4 *>(smem + S::kInfoOff);
-    uint64_t *const in_full = reinterpret_cast<uint64_t *>(smem + S::kBarOff);
-    uint64_t *const in_empty = in_full + kInStages;
-    uint64_t *const box_full = in_empty + kInStages;
-    uint64_t *const box_empty = box_full + kInfoStages;
-    int *const s_progress = reinterpret_cast<int *>(smem + S::kProgressOff);  // furthest frame any consumer warp of the CTA has reached
+    uint64_t *const full = reinterpret_cast<uint64_t *>(smem + S::kBarOff);
+    uint64_t *const empty = full + kStages;
+    volatile int *const s_progress = reinterpret_cast<volatile int *>(smem + S::kProgressOff);  // per scout: how far it has dispatched, in eighths of a frame
 
     // Roles are numbered from the TOP warp of the CTA down (the scheduler favours the higher warp ids when several
-    // warps are ready; the producer and the scouts are a handful of instructions per tile, but every consumer waits on them).
+    // warps are ready; the scouts are a handful of instructions per tile, but every consumer waits on them).
     const int warp = (kThreads / 32 - 1) - (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int tiles_xy = tiles_x * tiles_y;
     const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
@@ -318,109 +331,188 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     const uint64_t pol_box = pol_first, pol_gg = pol_first, pol_zero = pol_last;
 
     if (threadIdx.x == 0) {
-        s_progress[0] = 0;
-        for (int s = 0; s < kInStages; ++s) { tma::mbar_init(in_full + s, 1); tma::mbar_init(in_empty + s, kGroupWarps); }
-        for (int s = 0; s < kInfoStages; ++s) { tma::mbar_init(box_full + s, 1); tma::mbar_init(box_empty + s, kGroupWarps); }
+        s_progress[0] = 0; s_progress[1] = 0;
+        // full: the scout arrives twice -- once with the byte count of the TMA loads, once when the tile's frame is known
+        // to be zero-filled by every CTA; empty: one arrival per consumer warp of the group
+        for (int s = 0; s < kStages; ++s) { tma::mbar_init(full + s, 2); tma::mbar_init(empty + s, kGroupWarps); }
         tma::fence_barrier_init();
     }
     __syncthreads();
 
-    if (warp == 0) {
-        // ===== producer: warp map + grad_output tiles =====
+    if (warp < kScouts) {
+        // ===== scouts: scout w serves the iterations it = w, w + 2, ... = consumer group w =====
+        // Per tile: fetch the tile index, read the map tile from global memory and reduce it to the bounding box of its
+        // taps (the TMA load of the same tile then hits L2), wait for the ring stage, issue the three TMA loads (map,
+        // grad_output, frame box) on the stage's one barrier, and make sure the tile's frame has been zero-filled by every
+        // CTA before giving the stage its second arrival.  The consumers do none of this: between two tiles they wait on
+        // one mbarrier.
         if (lane == 0) {
             tma::prefetch_desc(&tp.map); tma::prefetch_desc(&tp.gout);
-            int it = 0;
-            TileWalk tw;
-            tw.init(blockIdx.x, gridDim.x, tiles_x, tiles_y);
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it, tw.next(tiles_x, tiles_y)) {
-                const int s = it % kInStages, ph = (it / kInStages) & 1;
-                tma::mbar_wait_relaxed(in_empty + s, ph ^ 1);
-                const TileCoord tc = tw.coord();
-                float *dst = reinterpret_cast<float *>(s_in + (size_t)s * S::kInBytes);
-                tma::mbar_arrive_expect_tx(in_full + s, S::kInBytes);
-                if (kInter) tma::load_3d_hint(dst, &tp.map, in_full + s, 2 * tc.w0, tc.h0, n_begin + tc.n, pol_first);
-                else tma::load_4d_hint(dst, &tp.map, in_full + s, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
-                tma::load_4d_hint(dst + kMapTileFloats, &tp.gout, in_full + s, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
-            }
+            if (kGgrid) { tma::prefetch_desc(&tp.box[0]); tma::prefetch_desc(&tp.box[1]); tma::prefetch_desc(&tp.box[2]); }
         }
-    } else if (warp <= kScouts) {
-        // ===== scouts (alternate tiles): map tile -> tap bounding box -> frame box load =====
-        if (kGgrid && lane == 0) { tma::prefetch_desc(&tp.box[0]); tma::prefetch_desc(&tp.box[1]); tma::prefetch_desc(&tp.box[2]); }
-        int it = warp - 1;
-        TileWalk tw;
-        tw.init(blockIdx.x + (warp - 1) * gridDim.x, kScouts * gridDim.x, tiles_x, tiles_y);
-        for (int t = blockIdx.x + (warp - 1) * gridDim.x; t < total_tiles; t += kScouts * gridDim.x, it += kScouts, tw.next(tiles_x, tiles_y)) {
-            const int is = it % kInStages, iph = (it / kInStages) & 1;
-            const int bs = it % kInfoStages, bph = (it / kInfoStages) & 1;
-            const TileCoord tc = tw.coord();
-            const int cols = min(kTW, g.Wo - tc.w0), rows = min(kTH, g.Ho - tc.h0);
-            tma::mbar_wait_relaxed(in_full + is, iph);
-            float xlo, xhi, ylo, yhi;
-            map_tile_range<kInter>(reinterpret_cast<const float *>(s_in + (size_t)is * S::kInBytes), rows, cols, lane, xlo, xhi, ylo, yhi);
-            tma::mbar_wait_relaxed(box_empty + bs, bph ^ 1);
-            if (lane == 0) {
-                int4 info = box_of_range<kBorder, kAlign>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
-                info.w = tc.n;
-                s_info[2 * bs] = info;
-                s_info[2 * bs + 1] = make_int4(tc.h0, tc.w0, 0, 0);
-                if (!kGgrid || (info.z & (kInfoFallback | kInfoEmpty))) tma::mbar_arrive(box_full + bs);
-                else {
-                    const int shape = info.z & 0xff;
-                    tma::mbar_arrive_expect_tx(box_full + bs, box_w(shape) * box_h(shape) * CS * 4);
-                    tma::load_4d_hint(s_box + (size_t)bs * S::kBoxBytes, &tp.box[shape], box_full + bs, info.x, info.y, 0, n_begin + tc.n, pol_box);
+        // The first 2 * kScouts tiles of a CTA are static, the rest comes from the launch's counter.  The scout works
+        // on tile `t` while the map of its next tile `t1` is on its way into L2 (a TMA prefetch: a global load that
+        // misses L2 takes ~3 us under this kernel's traffic, most of a tile time) and the index of the one after is
+        // being fetched.
+        const int stride = kScouts * (int)gridDim.x;
+        int t = blockIdx.x + warp * gridDim.x, t1 = t + stride;
+        auto map_of = [&](const TileCoord &c) {
+            return (const float *)grid.p + (int64_t)(n_begin + c.n) * grid.sN + (int64_t)c.h0 * grid.s1 + (int64_t)c.w0 * grid.s2;
+        };
+        auto is_full = [&](const TileCoord &c) { return c.w0 + kTW <= g.Wo && c.h0 + kTH <= g.Ho; };
+        auto prefetch_map = [&](const TileCoord &c) {
+            if (kInter) tma::prefetch_l2_3d(&tp.map, 2 * c.w0, c.h0, n_begin + c.n);
+            else tma::prefetch_l2_4d(&tp.map, c.w0, c.h0, 0, n_begin + c.n);
+        };
+        TileCoord tc = tile_coord(min(t, total_tiles - 1), tiles_x, tiles_xy);
+        int zero_seen = -1;  // frames [0, zero_seen] are known to be zero-filled by every CTA
+#ifdef PWS_EXP_CLOCKS
+        long long s_range = 0, s_wait = 0, s_issue = 0, s_zero = 0; int s_nowait = 0, s_n = 0;
+#endif
+        for (int it = warp;; it += kScouts) {
+            const int st = it % kStages, ph = (it / kStages) & 1;
+#ifdef PWS_EXP_CLOCKS
+            const long long q0 = clock64();
+#endif
+            if (t >= total_tiles) {
+                tma::mbar_wait_relaxed(empty + st, ph ^ 1);
+                if (lane == 0) {
+                    s_info[2 * st] = make_int4(0, 0, kInfoStop, 0);
+                    tma::mbar_arrive(full + st); tma::mbar_arrive(full + st);
+                    s_progress[warp] = INT_MAX - 4;  // out of tiles: let the zero-fill warp run to the end
                 }
+                break;
             }
-            __syncwarp();
+            int t2 = 0;
+            if (lane == 0) t2 = (int)atomicAdd(&g_tile_next[slot], 1u) + 2 * stride;  // the tile after the next
+            const TileCoord tc1 = tile_coord(min(t1, total_tiles - 1), tiles_x, tiles_xy);
+            if (lane == 0 && t1 < total_tiles) prefetch_map(tc1);
+            const bool full_tile = is_full(tc);
+            float xlo, xhi, ylo, yhi;
+            if (full_tile) {
+                MapRegs m;
+                map_tile_fetch<kInter>(map_of(tc), grid.s1, grid.s3, lane, m);
+                map_tile_reduce<kInter>(m, xlo, xhi, ylo, yhi);
+            } else {
+                map_tile_range_global<kInter>(map_of(tc), grid.s1, grid.s3, min(kTH, g.Ho - tc.h0), min(kTW, g.Wo - tc.w0), lane, xlo, xhi, ylo, yhi);
+            }
+            int4 info = box_of_range<kBorder, kAlign>(xlo, xhi, ylo, yhi, g.W, g.H, full_tile);
+            if (kGgrid && kSlotShape < kNumShapes - 1 && !(info.z & (kInfoFallback | kInfoEmpty)) && (info.z & 0xff) > kSlotShape)
+                info = make_int4(0, 0, kInfoFallback, 0);
+            info.w = tc.n;
+            const int progress = 8 * tc.n + (8 * (t - tc.n * tiles_xy)) / tiles_xy;  // in eighths of a frame
+            const bool want_box = kGgrid && !(info.z & (kInfoFallback | kInfoEmpty));
+            const int shape = info.z & 0xff;
+#ifdef PWS_EXP_CLOCKS
+            const long long q1 = clock64();
+#endif
+            tma::mbar_wait_relaxed(empty + st, ph ^ 1);
+#ifdef PWS_EXP_CLOCKS
+            const long long q2 = clock64();
+            long long q3 = q2;
+#endif
+            if (lane == 0) {
+                s_info[2 * st] = info;
+#ifdef PWS_EXP_CLOCKS
+                s_info[2 * st + 1] = make_int4(tc.h0, tc.w0, (int)clock64(), 0);
+#else
+                s_info[2 * st + 1] = make_int4(tc.h0, tc.w0, 0, 0);
+#endif
+                float *dst = reinterpret_cast<float *>(s_in + (size_t)st * S::kInBytes);
+                tma::mbar_arrive_expect_tx(full + st, S::kInBytes + (want_box ? box_w(shape) * box_h(shape) * CS * 4 : 0));
+                if (kInter) tma::load_3d_hint(dst, &tp.map, full + st, 2 * tc.w0, tc.h0, n_begin + tc.n, pol_first);
+                else tma::load_4d_hint(dst, &tp.map, full + st, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
+                tma::load_4d_hint(dst + kMapTileFloats, &tp.gout, full + st, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
+                if (want_box) tma::load_4d_hint(s_box + (size_t)st * S::kBoxBytes, &tp.box[shape], full + st, info.x, info.y, 0, n_begin + tc.n, pol_box);
+#ifdef PWS_EXP_CLOCKS
+                q3 = clock64();
+#endif
+                if (kGin) {
+                    s_progress[warp] = progress;  // the zero-fill warp keeps `zero_ahead` eighths ahead of the scouts
+                    if (tc.n > zero_seen) {
+                        while (ld_acquire(&g_zero_done[slot][tc.n]) < gridDim.x) __nanosleep(64);
+                        zero_seen = tc.n;
+                    }
+                }
+                tma::mbar_arrive(full + st);  // releases (cta scope) the acquire above to the consumers of the stage
+            }
+#ifdef PWS_EXP_CLOCKS
+            if (lane == 0) { s_range += q1 - q0; s_wait += q2 - q1; s_issue += q3 - q2; s_zero += clock64() - q3; s_nowait += (q2 - q1 < 200); ++s_n; }
+#endif
+            t = t1; tc = tc1;
+            t1 = __shfl_sync(0xffffffffu, t2, 0);
         }
+#ifdef PWS_EXP_CLOCKS
+        if (lane == 0 && (blockIdx.x % 49) == 0)
+            printf("scout cta %3d w %d: tiles %3d range %8lld wait_empty %8lld (no wait: %3d) issue %8lld zero %8lld\n", blockIdx.x, warp, s_n, s_range, s_wait, s_nowait, s_issue, s_zero);
+#endif
     } else if (warp == kZeroWarp) {
         // ===== zero-fill of grad_input, frame by frame, this CTA's 1/gridDim share, two frames ahead =====
         if (kGin) {
             const int64_t frame_vec = (int64_t)gin.sN / 4;  // float4 per frame (host-checked: sN % 4 == 0, base 16-byte aligned)
             const int64_t share = (frame_vec + gridDim.x - 1) / gridDim.x;
             const int64_t v0 = (int64_t)blockIdx.x * share, v1 = min(frame_vec, v0 + share);
+#ifdef PWS_EXP_CLOCKS
+            long long z_trig = 0, z_st = 0, z_fence = 0;
+#endif
             for (int f = 0; f < n_frames; ++f) {
-                while (*reinterpret_cast<volatile int *>(s_progress) + zero_ahead < 8 * f) __nanosleep(256);
+#ifdef PWS_EXP_CLOCKS
+                const long long z0 = clock64();
+#endif
+                while (max(s_progress[0], s_progress[1]) + zero_ahead < 8 * f) __nanosleep(256);
+#ifdef PWS_EXP_CLOCKS
+                const long long z1 = clock64();
+#endif
                 float4 *__restrict__ dst = reinterpret_cast<float4 *>((float *)gin.p + (int64_t)(n_begin + f) * gin.sN);
                 for (int64_t v = v0 + lane; v < v1; v += 32) tma::st_zero_v4_hint(dst + v, pol_zero);
+#ifdef PWS_EXP_CLOCKS
+                const long long z2 = clock64();
+#endif
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(&g_zero_done[slot][f], 1u);
+#ifdef PWS_EXP_CLOCKS
+                z_trig += z1 - z0; z_st += z2 - z1; z_fence += clock64() - z2;
+#endif
             }
+#ifdef PWS_EXP_CLOCKS
+            if (lane == 0 && (blockIdx.x % 49) == 0) printf("zclk cta %3d: trig %8lld store %8lld fence %8lld\n", blockIdx.x, z_trig, z_st, z_fence);
+#endif
         }
     } else {
-        // ===== consumers: group `grp` owns tiles it = grp, grp + 2, ...; a warp owns a 32 x 8 strip =====
-        const int cw = warp - 1 - kScouts, grp = cw / kGroupWarps, wg = cw % kGroupWarps;
+        // ===== consumers: group `grp` owns the iterations it = grp, grp + 2, ...; a warp owns a 32 x 4 strip of the tile =====
+        const int cw = warp - kScouts, grp = cw / kGroupWarps, wg = cw % kGroupWarps;
         const int col0 = (wg & 1) * 32, row0 = (wg >> 1) * kStripRows;
         Queue<CS> q;
         q.buf = s_queue + cw * kQueueCap;
         q.count = 0;
         const float gxm_in = (kAlign ? Wm1 : Wf) * 0.5f, gym_in = (kAlign ? Hm1 : Hf) * 0.5f;
-        int zero_seen = -1;  // frames [0, zero_seen] are known to be zero-filled by every CTA
-        int it = grp;
-        for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += kGroups * gridDim.x, it += kGroups) {
-            const int is = it % kInStages, iph = (it / kInStages) & 1;
-            const int bs = it % kInfoStages, bph = (it / kInfoStages) & 1;
-            // one warp of the group polls (the mbarriers and, on a new frame, the zero-fill counter of that frame);
-            // the others park on a hardware barrier and spin on nothing
-            if (wg == 0) {
-                tma::mbar_wait(in_full + is, iph);
-                tma::mbar_wait(box_full + bs, bph);
-                if (kGin) {
-                    const int f = s_info[2 * bs].w;
-                    if (lane == 0) {
-                        // progress of this CTA in eighths of a frame (the zero-fill warp keeps `zero_ahead` eighths ahead of it)
-                        atomicMax(s_progress, 8 * f + (8 * (t - f * tiles_xy)) / tiles_xy);
-                        if (f > zero_seen) {
-                            while (ld_relaxed(&g_zero_done[slot][f]) < gridDim.x) __nanosleep(64);
-                            __threadfence();
-                        }
-                    }
-                    zero_seen = f;
-                    __syncwarp();
-                }
-            }
+#ifdef PWS_EXP_CLOCKS
+        long long c_wait = 0, c_bar = 0, c_body = 0, lat_late = 0, slack_late = 0, slack_ok = 0;
+        int n_late = 0, n_ok = 0;
+#endif
+        for (int it = grp;; it += kGroups) {
+            const int is = it % kStages, bs = is, ph = (it / kStages) & 1;
+#ifdef PWS_EXP_CLOCKS
+            const long long k2 = clock64();
+#endif
+            // one warp of the group waits on the stage's mbarrier, the others park on a hardware barrier and spin on nothing
+            if (wg == 0) tma::mbar_wait(full + is, ph);
+#ifdef PWS_EXP_CLOCKS
+            const long long k3 = clock64();
+#endif
             tma::named_bar_sync(1 + grp, kGroupWarps * 32);
+#ifdef PWS_EXP_CLOCKS
+            const long long k4 = clock64();
+            c_wait += k3 - k2; c_bar += k4 - k3;
+            if (wg == 0 && !(s_info[2 * bs].z & kInfoStop)) {
+                const int issue = s_info[2 * bs + 1].z;
+                if (k3 - k2 > 300) { ++n_late; lat_late += (int)k3 - issue; slack_late += (int)k2 - issue; }
+                else { ++n_ok; slack_ok += (int)k2 - issue; }
+            }
+#endif
             const int4 info = s_info[2 * bs], where = s_info[2 * bs + 1];
+            if (info.z & kInfoStop) break;
             const int n = n_begin + info.w, h0 = where.x + row0, w0 = where.y + col0;
             const int shape = info.z & 0xff;
             const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
@@ -466,20 +558,26 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 queue_flush<CS>(q, gipk, lane, pol_last);
             }
             __syncwarp();
-            if (lane == 0) { tma::mbar_arrive(in_empty + is); tma::mbar_arrive(box_empty + bs); }
+            if (lane == 0) tma::mbar_arrive(empty + is);
+#ifdef PWS_EXP_CLOCKS
+            c_body += clock64() - k4;
+#endif
         }
-        if (kGin && lane == 0) atomicMax(s_progress, INT_MAX - 4);  // out of tiles: let the zero-fill warp run to the end
+#ifdef PWS_EXP_CLOCKS
+        if (lane == 0 && (blockIdx.x % 49) == 0 && (wg == 0 || wg == 5))
+            printf("clk cta %3d grp %d wg %d: wait %8lld bar %8lld body %8lld | late tiles %3d: latency %6lld slack %6lld | on-time tiles %3d: slack %6lld\n", blockIdx.x, grp, wg, c_wait, c_bar, c_body,
+                   n_late, n_late ? lat_late / n_late : 0, n_late ? slack_late / n_late : 0, n_ok, n_ok ? slack_ok / n_ok : 0);
+#endif
     }
-    if (kGin) {
-        __syncthreads();
-        // the last CTA to leave hands the counter slot back clean
-        if (threadIdx.x == 0) {
+    __syncthreads();
+    // the last CTA to leave hands the counter slot back clean
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&g_exit_count[slot], 1u) == gridDim.x - 1) {
+            if (kGin) for (int f = 0; f < n_frames; ++f) g_zero_done[slot][f] = 0u;
+            g_tile_next[slot] = 0u;
+            g_exit_count[slot] = 0u;
             __threadfence();
-            if (atomicAdd(&g_exit_count[slot], 1u) == gridDim.x - 1) {
-                for (int f = 0; f < n_frames; ++f) g_zero_done[slot][f] = 0u;
-                g_exit_count[slot] = 0u;
-                __threadfence();
-            }
         }
     }
 }
@@ -508,7 +606,7 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
     const int grid = total < sm_count() ? total : sm_count();
     const int n_frames = total / (tiles_x * tiles_y);
     const int slot = (int)(next_slot.fetch_add(1u, std::memory_order_relaxed) % kSyncSlots);
-    kern<<<grid, kThreads, S::kTotal, st>>>(tp, pb.in, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0, n_frames, slot, zero_ahead());
+    kern<<<grid, kThreads, S::kTotal, st>>>(tp, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0, n_frames, slot, zero_ahead());
     note_launch();
     note_kernel("bwd_tma");
     return true;

@@ -16,6 +16,9 @@
 // (violent maps) or whose map holds NaN/inf gather from global memory inside the same kernel.
 // Arithmetic is the ATen order of pws_common.cuh / pws_tile.cuh: results are bit-identical to the
 // other forward kernels.
+// kCL: the frame is a channels-last view (R/main_new.py:679-684,716: permute(0,3,1,2) of an HWC buffer).  The
+// box is then a (C*BW) x BH slab of the (C*W, H, N) array -- a pixel's channels sit in consecutive words, lanes
+// on consecutive pixels are 3 words apart (no bank conflict) -- and the output stays dense NCHW like ATen's.
 #include "pws_pipe.cuh"
 
 #include <cstdlib>
@@ -43,10 +46,10 @@ template <int CS> struct Smem {
 
 struct TmaParams {
     CUtensorMap map;                // planar: (Wo, Ho, 2, N) box (64,16,2,1); interleaved: (2Wo, Ho, N) box (128,16,1)
-    CUtensorMap box[kNumShapes];    // frame (W, H, C, N), box (BW, BH, CS, 1)
+    CUtensorMap box[kNumShapes];    // frame (W, H, C, N), box (BW, BH, CS, 1); channels-last: (C*W, H, N), box (CS*BW, BH, 1)
 };
 
-template <int CS, bool kBorder, bool kAlign, bool kInter>
+template <int CS, bool kBorder, bool kAlign, bool kInter, bool kCL>
 __global__ void __launch_bounds__(kThreads, 1)
 fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View out, const Geometry g,
                const int tiles_x, const int tiles_y, const int total_tiles)
@@ -107,15 +110,16 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
             map_tile_range<kInter>(s_map + ms * kMapTileFloats, rows, cols, lane, xlo, xhi, ylo, yhi);
             tma::mbar_wait_relaxed(box_empty + bs, bph ^ 1);
             if (lane == 0) {
-                int4 info = box_of_range<kBorder, kAlign>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
+                int4 info = box_of_range<kBorder, kAlign, kCL>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
                 info.w = tc.n;
                 s_info[2 * bs] = info;
                 s_info[2 * bs + 1] = make_int4(tc.h0, tc.w0, 0, 0);
                 if (info.z & (kInfoFallback | kInfoEmpty)) tma::mbar_arrive(box_full + bs);
                 else {
                     const int shape = info.z & 0xff;
-                    tma::mbar_arrive_expect_tx(box_full + bs, box_w(shape) * box_h(shape) * CS * 4);
-                    tma::load_4d(s_box + (size_t)bs * S::kBoxBytes, &tp.box[shape], box_full + bs, info.x, info.y, 0, tc.n);
+                    tma::mbar_arrive_expect_tx(box_full + bs, box_w_of<kCL>(shape) * box_h(shape) * CS * 4);
+                    if (kCL) tma::load_3d(s_box + (size_t)bs * S::kBoxBytes, &tp.box[shape], box_full + bs, CS * info.x, info.y, tc.n);
+                    else tma::load_4d(s_box + (size_t)bs * S::kBoxBytes, &tp.box[shape], box_full + bs, info.x, info.y, 0, tc.n);
                 }
             }
             __syncwarp();
@@ -135,14 +139,16 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
             TileCoord tc;
             tc.n = info.w; tc.h0 = where.x; tc.w0 = where.y;
             const int shape = info.z & 0xff;
-            const int pitch = box_w(shape);
-            const int plane = box_w(shape) * box_h(shape);
+            // element strides inside the box: next pixel, next row, next channel
+            constexpr int px = kCL ? CS : 1;
+            const int pitch = px * box_w_of<kCL>(shape);
+            const int plane = kCL ? 1 : box_w(shape) * box_h(shape);
             const float *bp = reinterpret_cast<const float *>(s_box + (size_t)bs * S::kBoxBytes);
             float *__restrict__ op = (float *)out.p + (int64_t)tc.n * out.sN + (int64_t)tc.h0 * out.s2 + tc.w0;
             const int o_ch = out.s1, o_row = out.s2;
 
             if (info.z & kInfoInterior) {
-                const int base = -(info.y * pitch + info.x);
+                const int base = -(info.y * pitch + info.x * px);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int r = wg * 2 + j;
@@ -158,15 +164,15 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
                         const float wx1 = fsub(ix, x0f), wx0 = fsub(x0f + 1.0f, ix);
                         const float wy1 = fsub(iy, y0f), wy0 = fsub(y0f + 1.0f, iy);
                         const float nw = fmul(wx0, wy0), ne = fmul(wx1, wy0), sw = fmul(wx0, wy1), se = fmul(wx1, wy1);
-                        const float *__restrict__ p0 = bp + (y0 * pitch + x0 + base);
+                        const float *__restrict__ p0 = bp + (y0 * pitch + x0 * px + base);
                         const float *__restrict__ p1 = p0 + pitch;
                         float *__restrict__ o = op + (r * o_row + x);
 #pragma unroll
                         for (int c = 0; c < CS; ++c) {
                             float acc = ffma(p0[c * plane], nw, 0.f);
-                            acc = ffma(p0[c * plane + 1], ne, acc);
+                            acc = ffma(p0[c * plane + px], ne, acc);
                             acc = ffma(p1[c * plane], sw, acc);
-                            acc = ffma(p1[c * plane + 1], se, acc);
+                            acc = ffma(p1[c * plane + px], se, acc);
                             o[c * o_ch] = acc;
                         }
                     }
@@ -174,7 +180,7 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
             } else {
                 const bool fallback = (info.z & kInfoFallback) != 0;
                 const float *__restrict__ ip = (const float *)in.p + (int64_t)tc.n * in.sN;
-                const int sH = in.s2, i_ch = in.s1;
+                const int sH = in.s2, i_ch = in.s1, sW = kCL ? in.s3 : 1;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int r = wg * 2 + j;
@@ -191,27 +197,27 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
                         make_taps(ix, iy, g.H, g.W, tp4);
                         float *__restrict__ o = op + (r * o_row + x);
                         if (!fallback) {
-                            const float *__restrict__ p0 = bp + ((tp4.y0 - info.y) * pitch + (tp4.x0 - info.x));
+                            const float *__restrict__ p0 = bp + ((tp4.y0 - info.y) * pitch + (tp4.x0 - info.x) * px);
 #pragma unroll
                             for (int c = 0; c < CS; ++c) {
                                 const float *__restrict__ pc = p0 + c * plane;
                                 float acc = 0.f;
                                 if (tp4.mask & 1u) acc = ffma(pc[0], tp4.nw, acc);
-                                if (tp4.mask & 2u) acc = ffma(pc[1], tp4.ne, acc);
+                                if (tp4.mask & 2u) acc = ffma(pc[px], tp4.ne, acc);
                                 if (tp4.mask & 4u) acc = ffma(pc[pitch], tp4.sw, acc);
-                                if (tp4.mask & 8u) acc = ffma(pc[pitch + 1], tp4.se, acc);
+                                if (tp4.mask & 8u) acc = ffma(pc[pitch + px], tp4.se, acc);
                                 o[c * o_ch] = acc;
                             }
                         } else {
-                            const float *__restrict__ p0 = ip + (tp4.y0 * sH + tp4.x0);
+                            const float *__restrict__ p0 = ip + (tp4.y0 * sH + tp4.x0 * sW);
 #pragma unroll
                             for (int c = 0; c < CS; ++c) {
                                 const float *__restrict__ pc = p0 + c * i_ch;
                                 float acc = 0.f;
                                 if (tp4.mask & 1u) acc = ffma(__ldg(pc), tp4.nw, acc);
-                                if (tp4.mask & 2u) acc = ffma(__ldg(pc + 1), tp4.ne, acc);
+                                if (tp4.mask & 2u) acc = ffma(__ldg(pc + sW), tp4.ne, acc);
                                 if (tp4.mask & 4u) acc = ffma(__ldg(pc + sH), tp4.sw, acc);
-                                if (tp4.mask & 8u) acc = ffma(__ldg(pc + sH + 1), tp4.se, acc);
+                                if (tp4.mask & 8u) acc = ffma(__ldg(pc + sH + sW), tp4.se, acc);
                                 o[c * o_ch] = acc;
                             }
                         }
@@ -224,10 +230,10 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
     }
 }
 
-template <int CS, bool kBorder, bool kAlign, bool kInter>
+template <int CS, bool kBorder, bool kAlign, bool kInter, bool kCL>
 bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, int total, cudaStream_t st)
 {
-    auto kern = fwd_tma_kernel<CS, kBorder, kAlign, kInter>;
+    auto kern = fwd_tma_kernel<CS, kBorder, kAlign, kInter, kCL>;
     static bool attr_done = false;  // per instantiation
     if (!attr_done) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<CS>::kTotal) != cudaSuccess) {
@@ -239,18 +245,18 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
     const int grid = total < sm_count() ? total : sm_count();
     kern<<<grid, kThreads, Smem<CS>::kTotal, st>>>(tp, pb.in, pb.out, pb.g, tiles_x, tiles_y, total);
     note_launch();
-    note_kernel("fwd_tma");
+    note_kernel(kCL ? "fwd_tma_cl" : "fwd_tma");
     return true;
 }
 
-template <int CS, bool kInter>
+template <int CS, bool kInter, bool kCL>
 bool launch_ba(const TmaParams &tp, const Problem &pb, int tx, int ty, int total, cudaStream_t st)
 {
     const bool border = pb.g.padding == PWS_PAD_BORDER, align = pb.g.align != 0;
-    if (border && align) return launch_k<CS, true, true, kInter>(tp, pb, tx, ty, total, st);
-    if (border) return launch_k<CS, true, false, kInter>(tp, pb, tx, ty, total, st);
-    if (align) return launch_k<CS, false, true, kInter>(tp, pb, tx, ty, total, st);
-    return launch_k<CS, false, false, kInter>(tp, pb, tx, ty, total, st);
+    if (border && align) return launch_k<CS, true, true, kInter, kCL>(tp, pb, tx, ty, total, st);
+    if (border) return launch_k<CS, true, false, kInter, kCL>(tp, pb, tx, ty, total, st);
+    if (align) return launch_k<CS, false, true, kInter, kCL>(tp, pb, tx, ty, total, st);
+    return launch_k<CS, false, false, kInter, kCL>(tp, pb, tx, ty, total, st);
 }
 
 }  // namespace
@@ -314,6 +320,18 @@ bool encode_frame_tma(const View &v, int W, int H, int C, int N, int bw, int bh,
     return tma::encode_f32(tm, v.p, 4, dims, strides, box);
 }
 
+// channels-last frame (element strides s1 == 1, s3 == C): (C*W, H, N) fp32 tensor map, box (C*bw, bh, 1)
+bool encode_frame_cl_tma(const View &v, int W, int H, int C, int N, int bw, int bh, CUtensorMap *tm)
+{
+    if (reinterpret_cast<uintptr_t>(v.p) & 15) return false;
+    if (v.s1 != 1 || v.s3 != C || (v.s2 % 4) || (v.sN % 4) || C * bw > 256) return false;
+    const uint64_t dims[3] = {(uint64_t)C * W, (uint64_t)H, (uint64_t)N};
+    const uint64_t sN = N > 1 ? (uint64_t)v.sN : (uint64_t)v.s2 * H;
+    const uint64_t strides[2] = {(uint64_t)v.s2, sN};
+    const uint32_t box[3] = {(uint32_t)(C * bw), (uint32_t)bh, 1};
+    return tma::encode_f32(tm, v.p, 3, dims, strides, box);
+}
+
 // Returns true when the TMA kernel took the call.
 bool launch_forward_tma(const Problem &pb, cudaStream_t st)
 {
@@ -329,10 +347,15 @@ bool launch_forward_tma(const Problem &pb, cudaStream_t st)
     TmaParams tp;
     bool inter = false;
     if (!encode_map_tma(pb.grid, g, &tp.map, &inter)) return false;
+    if (g.C == 3 && pb.in.s1 == 1 && pb.in.s3 == 3) {  // channels-last RGB (the inference site)
+        for (int s = 0; s < kNumShapes; ++s)
+            if (!encode_frame_cl_tma(pb.in, g.W, g.H, g.C, g.N, box_w_of<true>(s), box_h(s), &tp.box[s])) return false;
+        return inter ? launch_ba<3, true, true>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<3, false, true>(tp, pb, tiles_x, tiles_y, (int)total, st);
+    }
     for (int s = 0; s < kNumShapes; ++s)
         if (!encode_frame_tma(pb.in, g.W, g.H, g.C, g.N, box_w(s), box_h(s), g.C, &tp.box[s])) return false;
-    if (g.C == 3) return inter ? launch_ba<3, true>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<3, false>(tp, pb, tiles_x, tiles_y, (int)total, st);
-    return inter ? launch_ba<1, true>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<1, false>(tp, pb, tiles_x, tiles_y, (int)total, st);
+    if (g.C == 3) return inter ? launch_ba<3, true, false>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<3, false, false>(tp, pb, tiles_x, tiles_y, (int)total, st);
+    return inter ? launch_ba<1, true, false>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<1, false, false>(tp, pb, tiles_x, tiles_y, (int)total, st);
 }
 
 }  // namespace pws

@@ -161,3 +161,24 @@ def test_layouts_tma_cannot_describe_fall_back(pw):
     assert torch.equal(out, torch.ops.aten.grid_sampler_2d(frames, g, 0, 0, False))
     gi, gg = pw.warp2d_backward(gout, frames, g, 0, False, (True, True))
     assert last_kernel() in ("bwd_lean", "bwd_march")
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(1, 3, 1080, 1920, 1080, 1920)])
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+def test_tma_forward_channels_last_frames(pw, shape, pad):
+    # the inference site (R/main_new.py:679-684,716): the frame is permute(0,3,1,2) of an HWC buffer; the
+    # channels-last box path must equal ATen bit for bit and return a dense NCHW result like ATen does
+    N, C, H, W, Ho, Wo = shape
+    if C != 3:
+        pytest.skip("channels-last only differs from NCHW for C > 1")
+    for kind in ("smooth", "random", "noisy") if H < 1000 else ("smooth",):
+        for align in (False, True):
+            for layout in ("planar", "interleaved"):
+                frames, g, _ = make(kind, N, C, H, W, Ho, Wo, align, layout)
+                cl = frames.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+                assert cl.stride(1) == 1 and cl.stride(3) == C
+                out = pw.warp2d_forward(cl, g, PAD[pad], align)
+                assert last_kernel() == "fwd_tma_cl"
+                assert out.is_contiguous()
+                ref = torch.ops.aten.grid_sampler_2d(frames, g, 0, PAD[pad], align)
+                assert torch.equal(out, ref)
