@@ -15,13 +15,17 @@ constexpr int kTW = 64, kTH = 16;                      // output pixels per tile
 constexpr int kMapTileFloats = 2 * kTW * kTH;
 constexpr int kMapTileBytes = kMapTileFloats * 4;
 constexpr int kNumShapes = 3;
-constexpr int kBW0 = 72, kBH0 = 20, kBW1 = 80, kBH1 = 24, kBW2 = 88, kBH2 = 28;  // box shapes, smallest first
+// Box shapes, smallest first (pixels x rows; all channels).  27 rows, not 28: four such slots, six map tiles, four
+// grad_output tiles and the straggler queues of the backward then fit 227 KB.
+// (Measured and dropped: 96-wide boxes, whose row pitch is a multiple of the 32 banks.  They remove the 2-way bank
+// conflicts between lanes that sample different box rows -- 43 % of the backward's tap reads take a second wavefront --
+// but the extra box bytes and the lower height limit cost more than the conflicts: 0.480 vs 0.467 ms.)
+constexpr int kBW0 = 72, kBH0 = 20, kBW1 = 80, kBH1 = 24, kBW2 = 88, kBH2 = 27;
 constexpr int kMaxBW = kBW2, kMaxBH = kBH2;
 __host__ __device__ constexpr int box_w(int s) { return s == 0 ? kBW0 : s == 1 ? kBW1 : kBW2; }
 __host__ __device__ constexpr int box_h(int s) { return s == 0 ? kBH0 : s == 1 ? kBH1 : kBH2; }
 // channels-last RGB frames: the box is (3 * width) elements wide and a TMA box dimension holds at most 256
-constexpr int kBW2CL = 84;
-template <bool kCL> __host__ __device__ constexpr int box_w_of(int s) { return kCL && s == 2 ? kBW2CL : box_w(s); }
+template <bool kCL> __host__ __device__ constexpr int box_w_of(int s) { return kCL && s == 2 ? 84 : box_w(s); }
 
 // info.z of a tile: box shape in the low byte plus
 enum : int {
@@ -247,7 +251,7 @@ __device__ __forceinline__ int4 box_of_range(float xlo, float xhi, float ylo, fl
     const int bx = max(x0lo, 0) & ~3, by = max(y0lo, 0);
     const int bw = min(x0hi + 1, W - 1) - bx + 1, bh = min(y0hi + 1, H - 1) - by + 1;
     if (bw <= 0 || bh <= 0) return make_int4(0, 0, kInfoEmpty, 0);
-    const int shape = bw <= kBW0 && bh <= kBH0 ? 0 : bw <= kBW1 && bh <= kBH1 ? 1 : bw <= box_w_of<kCL>(2) && bh <= kBH2 ? 2 : -1;
+    const int shape = bw <= box_w_of<kCL>(0) && bh <= kBH0 ? 0 : bw <= box_w_of<kCL>(1) && bh <= kBH1 ? 1 : bw <= box_w_of<kCL>(2) && bh <= kBH2 ? 2 : -1;
     if (shape < 0) return make_int4(0, 0, kInfoFallback, 0);
     return make_int4(bx, by, shape | (interior ? kInfoInterior : 0), 0);
 }

@@ -64,7 +64,7 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
     return v;
 }
 constexpr int kStripRows = 2 * kTH / kGroupWarps;  // a warp owns a 32-column strip of this many rows
-constexpr int kQueueCap = 96;  // entries per consumer warp: 31 left over + 32 lanes x 2 east taps
+constexpr int kQueueCap = 64;  // entries per consumer warp: 31 left over + one class of stragglers from 32 lanes
 
 // ring depth and the largest box shape a ring slot holds (tiles that need a larger box gather from global memory)
 #ifndef PWS_BWD_STAGES
@@ -75,21 +75,25 @@ constexpr int kQueueCap = 96;  // entries per consumer warp: 31 left over + 32 l
 #endif
 constexpr int kSlotShape = PWS_BWD_SLOT_SHAPE;
 
-// One ring: a stage holds everything a tile needs -- its map + grad_output tile, its frame box, its info words --
-// behind one `full` and one `empty` mbarrier.
+// Two rings.  A stage of the main ring holds a tile's grad_output, its frame box and its info words behind one `full`
+// and one `empty` mbarrier.  The map tiles live in a ring of their own that is two slots deeper: a scout loads the
+// map of its NEXT tile while it dispatches the current one, so that the bounding box of a tile is known before the
+// tile's stage frees up and the grad_output and box loads leave the moment it does.
 template <int CS, bool kGgrid> struct Smem {
     static constexpr int kStages = kGgrid ? PWS_BWD_STAGES : 6;
-    static constexpr int kInBytes = kMapTileBytes + CS * kTW * kTH * 4;
-    static constexpr int kBoxBytes = kGgrid ? box_w(kSlotShape) * box_h(kSlotShape) * CS * 4 : 0;
-    static constexpr int kInOff = 0;
-    static constexpr int kBoxOff = kStages * kInBytes;
+    static constexpr int kMapStages = kStages + kScouts;
+    static constexpr int kGoutBytes = CS * kTW * kTH * 4;
+    static constexpr int kBoxBytes = kGgrid ? (box_w(kSlotShape) * box_h(kSlotShape) * CS * 4 + 127) / 128 * 128 : 0;
+    static constexpr int kMapOff = 0;
+    static constexpr int kGoutOff = kMapStages * kMapTileBytes;
+    static constexpr int kBoxOff = kGoutOff + kStages * kGoutBytes;
     static constexpr int kQueueOff = kBoxOff + kStages * kBoxBytes;
     static constexpr int kQueueEntry = CS == 3 ? 16 : 8;
     static constexpr int kInfoOff = kQueueOff + kConsumers * kQueueCap * kQueueEntry;
     static constexpr int kBarOff = kInfoOff + kStages * 32;
-    static constexpr int kProgressOff = kBarOff + 2 * kStages * 8;
+    static constexpr int kProgressOff = kBarOff + 2 * (kStages + kMapStages) * 8;
     static constexpr int kTotal = kProgressOff + 16;
-    static_assert(kInBytes % 128 == 0 && kBoxBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(kGoutBytes % 128 == 0 && kBoxBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
@@ -208,16 +212,28 @@ __device__ __forceinline__ void bwd_row(
 
     if (kGin) {
         const float nw = fmul(dw, dn), ne = fmul(de, dn), sw = fmul(dw, ds), se = fmul(de, ds);
-        const int px0 = __shfl_up_sync(0xffffffffu, x0, 1), py0 = __shfl_up_sync(0xffffffffu, y0, 1);
-        const int nx0 = __shfl_down_sync(0xffffffffu, x0, 1), ny0 = __shfl_down_sync(0xffffffffu, y0, 1);
-        bool take = lane > 0 && px0 + 1 == x0 && py0 == y0;
-        bool given = lane < 31 && nx0 == x0 + 1 && ny0 == y0;
-        if (kMasked) {
-            take = take && px_ok && ((live >> (lane - 1)) & 1u);
-            given = given && px_ok && ((live >> (lane + 1)) & 1u);
+        const int o_nw = y0 * W + x0;  // grad_input is dense NCHW
+        bool take, given;
+#ifndef PWS_BWD_SHFL4
+        if (!kMasked) {
+            // every tap is inside the frame, so x0 <= W - 2 and "left neighbour's offset + 1 == mine" can only mean the
+            // same row: one shuffle and one vote instead of four shuffles (lane l gives iff lane l + 1 takes)
+            const int o_left = __shfl_up_sync(0xffffffffu, o_nw, 1);
+            take = lane > 0 && o_left + 1 == o_nw;
+            given = ((__ballot_sync(0xffffffffu, take) >> 1) >> lane) & 1u;
+        } else
+#endif
+        {
+            const int px0 = __shfl_up_sync(0xffffffffu, x0, 1), py0 = __shfl_up_sync(0xffffffffu, y0, 1);
+            const int nx0 = __shfl_down_sync(0xffffffffu, x0, 1), ny0 = __shfl_down_sync(0xffffffffu, y0, 1);
+            take = lane > 0 && px0 + 1 == x0 && py0 == y0;
+            given = lane < 31 && nx0 == x0 + 1 && ny0 == y0;
+            if (kMasked) {
+                take = take && px_ok && ((live >> (lane - 1)) & 1u);
+                given = given && px_ok && ((live >> (lane + 1)) & 1u);
+            }
         }
         const bool chain = cy.live && cy.x == x0 && cy.y == y0;
-        const int o_nw = y0 * W + x0;  // grad_input is dense NCHW
         const int o_cy = cy.y * W + cy.x;
         // stragglers of this row -> queue: east taps nobody takes over (top and bottom), parked sums whose chain broke
         const bool p_e1 = !given && (mask & 2u), p_e2 = !given && (mask & 8u), p_f = cy.live && !chain;
@@ -238,18 +254,24 @@ __device__ __forceinline__ void bwd_row(
             // all taps valid: the two east classes share their predicate
             const unsigned b = __ballot_sync(0xffffffffu, p_e1);
             if (b) {
-                const int n = __popc(b), pos = q.count + __popc(b & lt);
-                if (p_e1) { queue_put<CS>(q, pos, o_nw + 1, etop); queue_put<CS>(q, pos + n, o_nw + W + 1, ebot); }
-                q.count += 2 * n;
+                const int n = __popc(b), rank = __popc(b & lt);
+                if (p_e1) queue_put<CS>(q, q.count + rank, o_nw + 1, etop);
+                q.count += n;
+                if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
+                if (p_e1) queue_put<CS>(q, q.count + rank, o_nw + W + 1, ebot);
+                q.count += n;
                 if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
             }
         } else {
             const unsigned b1 = __ballot_sync(0xffffffffu, p_e1), b2 = __ballot_sync(0xffffffffu, p_e2);
-            if (b1 | b2) {
-                const int n1 = __popc(b1), pos1 = q.count + __popc(b1 & lt), pos2 = q.count + n1 + __popc(b2 & lt);
-                if (p_e1) queue_put<CS>(q, pos1, o_nw + 1, etop);
-                if (p_e2) queue_put<CS>(q, pos2, o_nw + W + 1, ebot);
-                q.count += n1 + __popc(b2);
+            if (b1) {
+                if (p_e1) queue_put<CS>(q, q.count + __popc(b1 & lt), o_nw + 1, etop);
+                q.count += __popc(b1);
+                if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
+            }
+            if (b2) {
+                if (p_e2) queue_put<CS>(q, q.count + __popc(b2 & lt), o_nw + W + 1, ebot);
+                q.count += __popc(b2);
                 if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
             }
         }
@@ -308,14 +330,17 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                const int tiles_x, const int tiles_y, const int total_tiles, const int n_begin, const int n_frames, const int slot, const int zero_ahead)
 {
     using S = Smem<CS, kGgrid>;
-    constexpr int kStages = S::kStages;
+    constexpr int kStages = S::kStages, kMapStages = S::kMapStages;
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *const s_in = smem + S::kInOff;
+    float *const s_map = reinterpret_cast<float *>(smem + S::kMapOff);
+    unsigned char *const s_gout = smem + S::kGoutOff;
     unsigned char *const s_box = smem + S::kBoxOff;
     QEntry<CS> *const s_queue = reinterpret_cast<QEntry<CS> *>(smem + S::kQueueOff);
     int4 *const s_info = reinterpret_cast<int4 *>(smem + S::kInfoOff);
     uint64_t *const full = reinterpret_cast<uint64_t *>(smem + S::kBarOff);
     uint64_t *const empty = full + kStages;
+    uint64_t *const map_full = empty + kStages;
+    uint64_t *const map_empty = map_full + kMapStages;
     volatile int *const s_progress = reinterpret_cast<volatile int *>(smem + S::kProgressOff);  // per scout: how far it has dispatched, in eighths of a frame
 
     // Roles are numbered from the TOP warp of the CTA down (the scheduler favours the higher warp ids when several
@@ -335,42 +360,44 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
         // full: the scout arrives twice -- once with the byte count of the TMA loads, once when the tile's frame is known
         // to be zero-filled by every CTA; empty: one arrival per consumer warp of the group
         for (int s = 0; s < kStages; ++s) { tma::mbar_init(full + s, 2); tma::mbar_init(empty + s, kGroupWarps); }
+        for (int s = 0; s < kMapStages; ++s) { tma::mbar_init(map_full + s, 1); tma::mbar_init(map_empty + s, kGroupWarps); }
         tma::fence_barrier_init();
     }
     __syncthreads();
 
     if (warp < kScouts) {
         // ===== scouts: scout w serves the iterations it = w, w + 2, ... = consumer group w =====
-        // Per tile: fetch the tile index, read the map tile from global memory and reduce it to the bounding box of its
-        // taps (the TMA load of the same tile then hits L2), wait for the ring stage, issue the three TMA loads (map,
-        // grad_output, frame box) on the stage's one barrier, and make sure the tile's frame has been zero-filled by every
-        // CTA before giving the stage its second arrival.  The consumers do none of this: between two tiles they wait on
+        // Per tile: fetch the tile index, start the map load of the NEXT tile, reduce this tile's map (already in the map
+        // ring) to the bounding box of its taps, wait for the ring stage, issue the grad_output and frame box loads on the
+        // stage's barrier, and make sure the tile's frame has been zero-filled by every CTA before giving the stage its
+        // second arrival.  The consumers do none of this: between two tiles they wait on
         // one mbarrier.
         if (lane == 0) {
             tma::prefetch_desc(&tp.map); tma::prefetch_desc(&tp.gout);
             if (kGgrid) { tma::prefetch_desc(&tp.box[0]); tma::prefetch_desc(&tp.box[1]); tma::prefetch_desc(&tp.box[2]); }
         }
         // The first 2 * kScouts tiles of a CTA are static, the rest comes from the launch's counter.  The scout works
-        // on tile `t` while the map of its next tile `t1` is on its way into L2 (a TMA prefetch: a global load that
-        // misses L2 takes ~3 us under this kernel's traffic, most of a tile time) and the index of the one after is
-        // being fetched.
+        // on tile `t` while the map of its next tile `t1` is being loaded into the map ring and the index of the one
+        // after is being fetched.
         const int stride = kScouts * (int)gridDim.x;
         int t = blockIdx.x + warp * gridDim.x, t1 = t + stride;
-        auto map_of = [&](const TileCoord &c) {
-            return (const float *)grid.p + (int64_t)(n_begin + c.n) * grid.sN + (int64_t)c.h0 * grid.s1 + (int64_t)c.w0 * grid.s2;
-        };
-        auto is_full = [&](const TileCoord &c) { return c.w0 + kTW <= g.Wo && c.h0 + kTH <= g.Ho; };
-        auto prefetch_map = [&](const TileCoord &c) {
-            if (kInter) tma::prefetch_l2_3d(&tp.map, 2 * c.w0, c.h0, n_begin + c.n);
-            else tma::prefetch_l2_4d(&tp.map, c.w0, c.h0, 0, n_begin + c.n);
+        // map load of iteration `i` (tile coordinates c) into its slot of the map ring; lane 0 only
+        auto load_map = [&](int i, const TileCoord &c) {
+            const int ms = i % kMapStages;
+            tma::mbar_arrive_expect_tx(map_full + ms, kMapTileBytes);
+            if (kInter) tma::load_3d_hint(s_map + ms * kMapTileFloats, &tp.map, map_full + ms, 2 * c.w0, c.h0, n_begin + c.n, pol_first);
+            else tma::load_4d_hint(s_map + ms * kMapTileFloats, &tp.map, map_full + ms, c.w0, c.h0, 0, n_begin + c.n, pol_first);
         };
         TileCoord tc = tile_coord(min(t, total_tiles - 1), tiles_x, tiles_xy);
+        if (lane == 0 && t < total_tiles) load_map(warp, tc);  // the ring starts out empty
         int zero_seen = -1;  // frames [0, zero_seen] are known to be zero-filled by every CTA
 #ifdef PWS_EXP_CLOCKS
         long long s_range = 0, s_wait = 0, s_issue = 0, s_zero = 0; int s_nowait = 0, s_n = 0;
 #endif
         for (int it = warp;; it += kScouts) {
             const int st = it % kStages, ph = (it / kStages) & 1;
+            const int ms = it % kMapStages, mph = (it / kMapStages) & 1;
+            const int ms1 = (it + kScouts) % kMapStages, mph1 = ((it + kScouts) / kMapStages) & 1;
 #ifdef PWS_EXP_CLOCKS
             const long long q0 = clock64();
 #endif
@@ -386,17 +413,18 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             int t2 = 0;
             if (lane == 0) t2 = (int)atomicAdd(&g_tile_next[slot], 1u) + 2 * stride;  // the tile after the next
             const TileCoord tc1 = tile_coord(min(t1, total_tiles - 1), tiles_x, tiles_xy);
-            if (lane == 0 && t1 < total_tiles) prefetch_map(tc1);
-            const bool full_tile = is_full(tc);
-            float xlo, xhi, ylo, yhi;
-            if (full_tile) {
-                MapRegs m;
-                map_tile_fetch<kInter>(map_of(tc), grid.s1, grid.s3, lane, m);
-                map_tile_reduce<kInter>(m, xlo, xhi, ylo, yhi);
-            } else {
-                map_tile_range_global<kInter>(map_of(tc), grid.s1, grid.s3, min(kTH, g.Ho - tc.h0), min(kTW, g.Wo - tc.w0), lane, xlo, xhi, ylo, yhi);
+            // next tile's map: its slot was last used kMapStages iterations ago and is normally free by now
+            bool next_loaded = t1 >= total_tiles;
+            if (!next_loaded && __shfl_sync(0xffffffffu, (int)tma::mbar_test(map_empty + ms1, mph1 ^ 1), 0)) {
+                if (lane == 0) load_map(it + kScouts, tc1);
+                next_loaded = true;
             }
-            int4 info = box_of_range<kBorder, kAlign>(xlo, xhi, ylo, yhi, g.W, g.H, full_tile);
+            // this tile: bounding box of its taps from the map tile in shared memory
+            const int cols = min(kTW, g.Wo - tc.w0), rows = min(kTH, g.Ho - tc.h0);
+            tma::mbar_wait_relaxed(map_full + ms, mph);
+            float xlo, xhi, ylo, yhi;
+            map_tile_range<kInter>(s_map + ms * kMapTileFloats, rows, cols, lane, xlo, xhi, ylo, yhi);
+            int4 info = box_of_range<kBorder, kAlign>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
             if (kGgrid && kSlotShape < kNumShapes - 1 && !(info.z & (kInfoFallback | kInfoEmpty)) && (info.z & 0xff) > kSlotShape)
                 info = make_int4(0, 0, kInfoFallback, 0);
             info.w = tc.n;
@@ -418,11 +446,8 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
 #else
                 s_info[2 * st + 1] = make_int4(tc.h0, tc.w0, 0, 0);
 #endif
-                float *dst = reinterpret_cast<float *>(s_in + (size_t)st * S::kInBytes);
-                tma::mbar_arrive_expect_tx(full + st, S::kInBytes + (want_box ? box_w(shape) * box_h(shape) * CS * 4 : 0));
-                if (kInter) tma::load_3d_hint(dst, &tp.map, full + st, 2 * tc.w0, tc.h0, n_begin + tc.n, pol_first);
-                else tma::load_4d_hint(dst, &tp.map, full + st, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
-                tma::load_4d_hint(dst + kMapTileFloats, &tp.gout, full + st, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
+                tma::mbar_arrive_expect_tx(full + st, S::kGoutBytes + (want_box ? box_w(shape) * box_h(shape) * CS * 4 : 0));
+                tma::load_4d_hint(s_gout + (size_t)st * S::kGoutBytes, &tp.gout, full + st, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
                 if (want_box) tma::load_4d_hint(s_box + (size_t)st * S::kBoxBytes, &tp.box[shape], full + st, info.x, info.y, 0, n_begin + tc.n, pol_box);
 #ifdef PWS_EXP_CLOCKS
                 q3 = clock64();
@@ -434,7 +459,12 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                         zero_seen = tc.n;
                     }
                 }
-                tma::mbar_arrive(full + st);  // releases (cta scope) the acquire above to the consumers of the stage
+                // second arrival: passes on (cta scope) the acquire above and this scout's view of the map tile
+                tma::mbar_arrive(full + st);
+            }
+            if (!next_loaded) {
+                tma::mbar_wait_relaxed(map_empty + ms1, mph1 ^ 1);
+                if (lane == 0) load_map(it + kScouts, tc1);
             }
 #ifdef PWS_EXP_CLOCKS
             if (lane == 0) { s_range += q1 - q0; s_wait += q2 - q1; s_issue += q3 - q2; s_zero += clock64() - q3; s_nowait += (q2 - q1 < 200); ++s_n; }
@@ -497,11 +527,17 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             const long long k2 = clock64();
 #endif
             // one warp of the group waits on the stage's mbarrier, the others park on a hardware barrier and spin on nothing
+#ifdef PWS_BWD_NOBAR
+            tma::mbar_wait(full + is, ph);
+#else
             if (wg == 0) tma::mbar_wait(full + is, ph);
+#endif
 #ifdef PWS_EXP_CLOCKS
             const long long k3 = clock64();
 #endif
+#ifndef PWS_BWD_NOBAR
             tma::named_bar_sync(1 + grp, kGroupWarps * 32);
+#endif
 #ifdef PWS_EXP_CLOCKS
             const long long k4 = clock64();
             c_wait += k3 - k2; c_bar += k4 - k3;
@@ -516,8 +552,9 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             const int n = n_begin + info.w, h0 = where.x + row0, w0 = where.y + col0;
             const int shape = info.z & 0xff;
             const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
-            const float *mp = reinterpret_cast<const float *>(s_in + (size_t)is * S::kInBytes);
-            const float *gop = mp + kMapTileFloats + row0 * kTW + col0 + lane;
+            const int ms = it % kMapStages;
+            const float *mp = s_map + ms * kMapTileFloats;
+            const float *gop = reinterpret_cast<const float *>(s_gout + (size_t)is * S::kGoutBytes) + row0 * kTW + col0 + lane;
             const float *bp = reinterpret_cast<const float *>(s_box + (size_t)bs * S::kBoxBytes) - (info.y * pitch + info.x);
             const float *__restrict__ ip = (const float *)in.p + (int64_t)n * in.sN;
             float *gipk[CS];  // per-channel planes of this frame's grad_input (dense NCHW)
@@ -558,7 +595,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 queue_flush<CS>(q, gipk, lane, pol_last);
             }
             __syncwarp();
-            if (lane == 0) tma::mbar_arrive(empty + is);
+            if (lane == 0) { tma::mbar_arrive(empty + is); tma::mbar_arrive(map_empty + ms); }
 #ifdef PWS_EXP_CLOCKS
             c_body += clock64() - k4;
 #endif
