@@ -125,6 +125,12 @@ __device__ __forceinline__ void load_4d_hint(void *dst, const CUtensorMap *tm, u
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
 }
+// fire-and-forget float add (no L2 policy operand: the default priority needs none, and a policy costs the SASS two
+// R2UR per instruction for the descriptor)
+__device__ __forceinline__ void red_add_f32(float *p, float v)
+{
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 __device__ __forceinline__ void st_f32_hint(float *p, float v, uint64_t pol)
 {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");

@@ -29,11 +29,11 @@ using namespace pipe;
 namespace {
 
 #ifdef PWS_EXP_NORED   // experiment: drop the scatter's atomics (results are wrong) to time everything else
-#define PWS_RED(p, v) do { if ((v) == 1.2345e-30f) tma::st_f32_hint((p), (v), pol_last); } while (0)
+#define PWS_RED(p, v) do { if ((v) == 1.2345e-30f) tma::red_add_f32((p), (v)); } while (0)
 #else
 // explicit fire-and-forget reduction: with a fence elsewhere in the kernel nvcc turns atomicAdd into the
 // returning ATOMG form, whose round trip to L2 the scatter would then wait for
-#define PWS_RED(p, v) tma::red_add_f32_hint((p), (v), pol_last)
+#define PWS_RED(p, v) tma::red_add_f32((p), (v))
 #endif
 
 #ifndef PWS_BWD_UNROLL
@@ -127,35 +127,36 @@ __device__ __forceinline__ void queue_put(Queue<CS> &q, int pos, int off, const 
     else *reinterpret_cast<int2 *>(q.buf + pos) = make_int2(off, __float_as_int(v[0]));
 }
 template <int CS>
-__device__ __forceinline__ void queue_pop_red(const Queue<CS> &q, int pos, float *const (&gipk)[CS], const uint64_t pol_last)
+__device__ __forceinline__ void queue_pop_red(const Queue<CS> &q, int pos, float *const gip0, const int64_t gs1, const uint64_t pol_last)
 {
     if (CS == 3) {
         const int4 e = *reinterpret_cast<const int4 *>(q.buf + pos);
-        PWS_RED(gipk[0] + e.x, __int_as_float(e.y));
-        PWS_RED(gipk[CS > 1 ? 1 : 0] + e.x, __int_as_float(e.z));
-        PWS_RED(gipk[CS > 2 ? 2 : 0] + e.x, __int_as_float(e.w));
+        float *const p = gip0 + e.x;  // the three channel planes of one source pixel
+        PWS_RED(p, __int_as_float(e.y));
+        PWS_RED(p + gs1, __int_as_float(e.z));
+        PWS_RED(p + 2 * gs1, __int_as_float(e.w));
     } else {
         const int2 e = *reinterpret_cast<const int2 *>(q.buf + pos);
-        PWS_RED(gipk[0] + e.x, __int_as_float(e.y));
+        PWS_RED(gip0 + e.x, __int_as_float(e.y));
     }
 }
 // dense 32-lane REDs while at least a warp's worth of entries is queued
 template <int CS>
-__device__ __forceinline__ void queue_drain(Queue<CS> &q, float *const (&gipk)[CS], int lane, const uint64_t pol_last)
+__device__ __forceinline__ void queue_drain(Queue<CS> &q, float *const gip0, const int64_t gs1, int lane, const uint64_t pol_last)
 {
     __syncwarp();
 #pragma unroll 1
     while (q.count >= 32) {
-        queue_pop_red<CS>(q, q.count - 32 + lane, gipk, pol_last);
+        queue_pop_red<CS>(q, q.count - 32 + lane, gip0, gs1, pol_last);
         q.count -= 32;
     }
     __syncwarp();
 }
 template <int CS>
-__device__ __forceinline__ void queue_flush(Queue<CS> &q, float *const (&gipk)[CS], int lane, const uint64_t pol_last)
+__device__ __forceinline__ void queue_flush(Queue<CS> &q, float *const gip0, const int64_t gs1, int lane, const uint64_t pol_last)
 {
-    queue_drain<CS>(q, gipk, lane, pol_last);
-    if (lane < q.count) queue_pop_red<CS>(q, lane, gipk, pol_last);
+    queue_drain<CS>(q, gip0, gs1, lane, pol_last);
+    if (lane < q.count) queue_pop_red<CS>(q, lane, gip0, gs1, pol_last);
     q.count = 0;
     __syncwarp();
 }
@@ -169,7 +170,7 @@ __device__ __forceinline__ void bwd_row(
     const float gxm, const float gym, const float (&go)[CS],
     const float *__restrict__ box, const int pitch, const int plane,
     const float *__restrict__ ip, const int sH, const int i_ch, const int H, const int W,
-    float *const (&gipk)[CS],
+    float *const gip0, const int64_t gs1,
     float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy, Queue<CS> &q, const uint64_t pol_last, const uint64_t pol_first)
 {
     const float dw = fsub(x0f + 1.0f, ix), de = fsub(ix, x0f), dn = fsub(y0f + 1.0f, iy), ds = fsub(iy, y0f);
@@ -247,7 +248,7 @@ __device__ __forceinline__ void bwd_row(
             if (take) { top += ptop; bot += pbot; }
             brk[k] = cy.v[k];
             if (chain) top += cy.v[k];
-            if (mask & 1u) PWS_RED(gipk[k] + o_nw, top);
+            if (mask & 1u) PWS_RED(gip0 + o_nw + k * gs1, top);
             cy.v[k] = bot;
         }
         if (!kMasked) {
@@ -257,22 +258,22 @@ __device__ __forceinline__ void bwd_row(
                 const int n = __popc(b), rank = __popc(b & lt);
                 if (p_e1) queue_put<CS>(q, q.count + rank, o_nw + 1, etop);
                 q.count += n;
-                if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
+                if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
                 if (p_e1) queue_put<CS>(q, q.count + rank, o_nw + W + 1, ebot);
                 q.count += n;
-                if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
+                if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
             }
         } else {
             const unsigned b1 = __ballot_sync(0xffffffffu, p_e1), b2 = __ballot_sync(0xffffffffu, p_e2);
             if (b1) {
                 if (p_e1) queue_put<CS>(q, q.count + __popc(b1 & lt), o_nw + 1, etop);
                 q.count += __popc(b1);
-                if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
+                if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
             }
             if (b2) {
                 if (p_e2) queue_put<CS>(q, q.count + __popc(b2 & lt), o_nw + W + 1, ebot);
                 q.count += __popc(b2);
-                if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
+                if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
             }
         }
         {
@@ -281,7 +282,7 @@ __device__ __forceinline__ void bwd_row(
                 const int pos = q.count + __popc(b & lt);
                 if (p_f) queue_put<CS>(q, pos, o_cy, brk);
                 q.count += __popc(b);
-                if (q.count >= 32) queue_drain<CS>(q, gipk, lane, pol_last);
+                if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
             }
         }
         cy.x = x0; cy.y = y0 + 1;
@@ -295,7 +296,7 @@ __device__ __forceinline__ void masked_strip(
     const int lane, const int4 info, const int h0, const int w0, const int row0, const int col0,
     const float *__restrict__ mp, const float *__restrict__ gop, const float *__restrict__ bp, const int pitch, const int plane,
     const float *__restrict__ ip, const int sH, const int i_ch, const Geometry g,
-    float *const (&gipk)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Carry<CS> &cy, Queue<CS> &q,
+    float *const gip0, const int64_t gs1, float *__restrict__ ggq, const int gg_s1, const int gg_s3, Carry<CS> &cy, Queue<CS> &q,
     const uint64_t pol_last, const uint64_t pol_first)
 {
     const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
@@ -316,10 +317,10 @@ __device__ __forceinline__ void masked_strip(
         const int x0 = (int)x0f, y0 = (int)y0f;
         if (box_taps)
             bwd_row<CS, kGin, kGgrid, true, true>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
-                                                   bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gipk, ggq, gg_s3, cy, q, pol_last, pol_first);
+                                                   bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gip0, gs1, ggq, gg_s3, cy, q, pol_last, pol_first);
         else
             bwd_row<CS, kGin, kGgrid, true, false>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
-                                                    bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gipk, ggq, gg_s3, cy, q, pol_last, pol_first);
+                                                    bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gip0, gs1, ggq, gg_s3, cy, q, pol_last, pol_first);
         if (kGgrid) ggq += gg_s1;
     }
 }
@@ -557,9 +558,8 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             const float *gop = reinterpret_cast<const float *>(s_gout + (size_t)is * S::kGoutBytes) + row0 * kTW + col0 + lane;
             const float *bp = reinterpret_cast<const float *>(s_box + (size_t)bs * S::kBoxBytes) - (info.y * pitch + info.x);
             const float *__restrict__ ip = (const float *)in.p + (int64_t)n * in.sN;
-            float *gipk[CS];  // per-channel planes of this frame's grad_input (dense NCHW)
-#pragma unroll
-            for (int k = 0; k < CS; ++k) gipk[k] = kGin ? (float *)gin.p + ((int64_t)n * gin.sN + (int64_t)k * gin.s1) : nullptr;
+            float *const gip0 = kGin ? (float *)gin.p + (int64_t)n * gin.sN : nullptr;  // this frame's grad_input (dense NCHW)
+            const int64_t gs1 = gin.s1;                                               // its channel stride
             float *__restrict__ ggq = kGgrid ? (float *)ggrid.p + (int64_t)n * ggrid.sN + (int64_t)h0 * ggrid.s1 + (int64_t)(w0 + lane) * ggrid.s2 : nullptr;
 
             Carry<CS> cy;
@@ -579,20 +579,20 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                     float x0f, y0f; int x0, y0;
                     floor_small(ix, x0f, x0); floor_small(iy, y0f, y0);
                     bwd_row<CS, kGin, kGgrid, false, true>(lane, true, 0xffffffffu, ix, iy, x0f, y0f, x0, y0, gxm_in, gym_in, go,
-                                                            bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gipk, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
+                                                            bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gip0, gs1, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
                     if (kGgrid) ggq += ggrid.s1;
                 }
             } else {
                 masked_strip<CS, kBorder, kAlign, kInter, kGin, kGgrid>(lane, info, h0, w0, row0, col0, mp, gop, bp, pitch, plane, ip, in.s2, in.s1,
-                                                                        g, gipk, ggq, ggrid.s1, ggrid.s3, cy, q, pol_last, pol_gg);
+                                                                        g, gip0, gs1, ggq, ggrid.s1, ggrid.s3, cy, q, pol_last, pol_gg);
             }
             if (kGin) {
                 if (cy.live) {
                     const int o_cy = cy.y * g.W + cy.x;
 #pragma unroll
-                    for (int k = 0; k < CS; ++k) PWS_RED(gipk[k] + o_cy, cy.v[k]);
+                    for (int k = 0; k < CS; ++k) PWS_RED(gip0 + o_cy + k * gs1, cy.v[k]);
                 }
-                queue_flush<CS>(q, gipk, lane, pol_last);
+                queue_flush<CS>(q, gip0, gs1, lane, pol_last);
             }
             __syncwarp();
             if (lane == 0) { tma::mbar_arrive(empty + is); tma::mbar_arrive(map_empty + ms); }
