@@ -251,6 +251,7 @@ __device__ __forceinline__ void bwd_row(
             if (mask & 1u) PWS_RED(gip0 + o_nw + k * gs1, top);
             cy.v[k] = bot;
         }
+#ifndef PWS_EXP_NOQUEUE   // experiment: drop the stragglers (results are wrong) to time the queue's share of a row
         if (!kMasked) {
             // all taps valid: the two east classes share their predicate
             const unsigned b = __ballot_sync(0xffffffffu, p_e1);
@@ -285,6 +286,7 @@ __device__ __forceinline__ void bwd_row(
                 if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
             }
         }
+#endif
         cy.x = x0; cy.y = y0 + 1;
         cy.live = (mask & 4u) != 0u;
     }
