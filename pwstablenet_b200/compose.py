@@ -102,6 +102,17 @@ def warp_fused(frame: torch.Tensor, drift: Optional[torch.Tensor] = None, base: 
         raise NotImplementedError("warp_fused: padding_mode must be 'zeros' or 'border'")
     n, c = frame.size(0), frame.size(1)
     keep = []
+    if upsample is not None and base != "none":
+        # Upsampling evaluates the lattice (drift + base) at four nodes per output pixel, and a base costs IEEE
+        # divisions per node.  Compose the low-resolution lattice once (what netG itself returns in the reference,
+        # 0.5 MB per frame at 256 x 256) and let the sampling kernel upsample that: same arithmetic per node, so the
+        # result is bit-identical, and the full-resolution map still never exists.
+        if map_size is None:
+            map_size = (drift.size(1), drift.size(2)) if drift is not None else None
+        if map_size is None:
+            raise RuntimeError("warp_fused: map_size is required when there is no drift")
+        drift = compose_map(n, map_size, drift, base, theta, base_align_corners, None, map_size, device=frame.device)
+        base, theta = "none", None
     spec = _spec(n, drift, base, theta, base_align_corners, upsample, map_size, pre, post, keep)
     if out_size is None:
         out_size = (spec.map_h, spec.map_w)
