@@ -228,7 +228,8 @@ __device__ __forceinline__ void map_tile_range_global(const float *__restrict__ 
 
 // From the extremes of a tile's map to the box of the frame its taps need: (bx, by, shape | flags).
 // unnormalise is monotone, so the extremes of the map give the extremes of the taps.
-template <bool kBorder, bool kAlign, bool kCL = false>
+// kXAlign: pixels per 16 bytes of a frame row (4 for fp32, 8 for 16-bit frames) -- TMA wants the box start aligned
+template <bool kBorder, bool kAlign, bool kCL = false, int kXAlign = 4>
 __device__ __forceinline__ int4 box_of_range(float xlo, float xhi, float ylo, float yhi, int W, int H, bool full_tile)
 {
     const float Wf = (float)W, Hf = (float)H, Wm1 = (float)(W - 1), Hm1 = (float)(H - 1);
@@ -248,7 +249,7 @@ __device__ __forceinline__ int4 box_of_range(float xlo, float xhi, float ylo, fl
     }
     // taps outside the frame are never read: clamp the box to the frame.
     // TMA wants the box start 16-byte aligned: x rounds down to a multiple of 4 elements.
-    const int bx = max(x0lo, 0) & ~3, by = max(y0lo, 0);
+    const int bx = max(x0lo, 0) & ~(kXAlign - 1), by = max(y0lo, 0);
     const int bw = min(x0hi + 1, W - 1) - bx + 1, bh = min(y0hi + 1, H - 1) - by + 1;
     if (bw <= 0 || bh <= 0) return make_int4(0, 0, kInfoEmpty, 0);
     const int shape = bw <= box_w_of<kCL>(0) && bh <= kBH0 ? 0 : bw <= box_w_of<kCL>(1) && bh <= kBH1 ? 1 : bw <= box_w_of<kCL>(2) && bh <= kBH2 ? 2 : -1;
@@ -260,7 +261,7 @@ __device__ __forceinline__ int4 box_of_range(float xlo, float xhi, float ylo, fl
 
 // host side (warp_fwd_tma.cu)
 bool encode_map_tma(const View &grid, const Geometry &g, CUtensorMap *tm, bool *inter);
-bool encode_frame_tma(const View &v, int W, int H, int C, int N, int bw, int bh, int bc, CUtensorMap *tm);
+bool encode_frame_tma(const View &v, int W, int H, int C, int N, int bw, int bh, int bc, CUtensorMap *tm, int dtype = PWS_F32);
 bool tma_disabled();
 int sm_count();
 

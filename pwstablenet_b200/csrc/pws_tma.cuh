@@ -201,17 +201,25 @@ inline EncodeTiledFn encode_fn()
 // General fp32 tiled map: `rank` dims (fastest first), element strides of dims 1..rank-1, box extents.
 // Requirements (the encoder rejects violations): base 16-byte aligned, every stride a multiple of 4
 // elements, box[0] a multiple of 4, every box extent <= 256.
-inline bool encode_f32(CUtensorMap *tm, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_elems,
-                       const uint32_t *box, CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B)
+// elem_bytes = 4 (fp32) or 2 (dtype16: CU_TENSOR_MAP_DATA_TYPE_FLOAT16 / _BFLOAT16): for 16-bit elements the
+// alignment rules read "8 elements" instead of "4".
+inline bool encode_elems(CUtensorMap *tm, CUtensorMapDataType dt, int elem_bytes, const void *base, int rank, const uint64_t *dims,
+                         const uint64_t *strides_elems, const uint32_t *box,
+                         CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn || rank < 1 || rank > 5) return false;
     cuuint64_t d[5], st[4];
     cuuint32_t b[5], es[5];
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
-    for (int i = 0; i + 1 < rank; ++i) st[i] = strides_elems[i] * 4;
-    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), d, st, b, es,
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides_elems[i] * (uint64_t)elem_bytes;
+    return fn(tm, dt, (cuuint32_t)rank, const_cast<void *>(base), d, st, b, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool encode_f32(CUtensorMap *tm, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_elems,
+                       const uint32_t *box, CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B)
+{
+    return encode_elems(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rank, dims, strides_elems, box, promo);
 }
 
 // rank-3 tiled map over (d0 fastest, d1, d2) with element strides s1, s2 (s0 == 1); elem = 4 bytes.

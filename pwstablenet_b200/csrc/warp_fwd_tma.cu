@@ -39,8 +39,8 @@ constexpr int kThreads = (1 + kScouts + kConsumers) * 32;
 #endif
 constexpr int kMapStages = PWS_FWD_MAP_STAGES, kBoxStages = PWS_FWD_BOX_STAGES;
 
-template <int CS> struct Smem {
-    static constexpr int kBoxBytes = (kMaxBW * kMaxBH * CS * 4 + 127) / 128 * 128;
+template <int CS, int kElem = 4> struct Smem {
+    static constexpr int kBoxBytes = (kMaxBW * kMaxBH * CS * kElem + 127) / 128 * 128;
     static constexpr int kMapOff = 0;
     static constexpr int kBoxOff = kMapStages * kMapTileBytes;
     static constexpr int kInfoOff = kBoxOff + kBoxStages * kBoxBytes;
@@ -55,12 +55,15 @@ struct TmaParams {
     CUtensorMap box[kNumShapes];    // frame (W, H, C, N), box (BW, BH, CS, 1); channels-last: (C*W, H, N), box (CS*BW, BH, 1)
 };
 
-template <int CS, bool kBorder, bool kAlign, bool kInter, bool kCL>
+// T: frame / output element (float; __half or __nv_bfloat16 with fp32 maps: taps are upcast, the arithmetic is fp32,
+// the result is rounded once -- the upcast-sample-round semantics of the other 16-bit kernels)
+template <typename T, int CS, bool kBorder, bool kAlign, bool kInter, bool kCL>
 __global__ void __launch_bounds__(kThreads, 1)
 fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View out, const Geometry g,
                const int tiles_x, const int tiles_y, const int total_tiles)
 {
-    using S = Smem<CS>;
+    using S = Smem<CS, (int)sizeof(T)>;
+    constexpr int kXAlign = 16 / (int)sizeof(T);
     extern __shared__ __align__(1024) unsigned char smem[];
     float *const s_map = reinterpret_cast<float *>(smem + S::kMapOff);
     unsigned char *const s_box = smem + S::kBoxOff;
@@ -116,14 +119,14 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
             map_tile_range<kInter>(s_map + ms * kMapTileFloats, rows, cols, lane, xlo, xhi, ylo, yhi);
             tma::mbar_wait_relaxed(box_empty + bs, bph ^ 1);
             if (lane == 0) {
-                int4 info = box_of_range<kBorder, kAlign, kCL>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
+                int4 info = box_of_range<kBorder, kAlign, kCL, kXAlign>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
                 info.w = tc.n;
                 s_info[2 * bs] = info;
                 s_info[2 * bs + 1] = make_int4(tc.h0, tc.w0, 0, 0);
                 if (info.z & (kInfoFallback | kInfoEmpty)) tma::mbar_arrive(box_full + bs);
                 else {
                     const int shape = info.z & 0xff;
-                    tma::mbar_arrive_expect_tx(box_full + bs, box_w_of<kCL>(shape) * box_h(shape) * CS * 4);
+                    tma::mbar_arrive_expect_tx(box_full + bs, box_w_of<kCL>(shape) * box_h(shape) * CS * (int)sizeof(T));
                     if (kCL) tma::load_3d(s_box + (size_t)bs * S::kBoxBytes, &tp.box[shape], box_full + bs, CS * info.x, info.y, tc.n);
                     else tma::load_4d(s_box + (size_t)bs * S::kBoxBytes, &tp.box[shape], box_full + bs, info.x, info.y, 0, tc.n);
                 }
@@ -149,8 +152,8 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
             constexpr int px = kCL ? CS : 1;
             const int pitch = px * box_w_of<kCL>(shape);
             const int plane = kCL ? 1 : box_w(shape) * box_h(shape);
-            const float *bp = reinterpret_cast<const float *>(s_box + (size_t)bs * S::kBoxBytes);
-            float *__restrict__ op = (float *)out.p + (int64_t)tc.n * out.sN + (int64_t)tc.h0 * out.s2 + tc.w0;
+            const T *bp = reinterpret_cast<const T *>(s_box + (size_t)bs * S::kBoxBytes);
+            T *__restrict__ op = (T *)out.p + (int64_t)tc.n * out.sN + (int64_t)tc.h0 * out.s2 + tc.w0;
             const int o_ch = out.s1, o_row = out.s2;
 
             if (info.z & kInfoInterior) {
@@ -170,22 +173,22 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
                         const float wx1 = fsub(ix, x0f), wx0 = fsub(x0f + 1.0f, ix);
                         const float wy1 = fsub(iy, y0f), wy0 = fsub(y0f + 1.0f, iy);
                         const float nw = fmul(wx0, wy0), ne = fmul(wx1, wy0), sw = fmul(wx0, wy1), se = fmul(wx1, wy1);
-                        const float *__restrict__ p0 = bp + (y0 * pitch + x0 * px + base);
-                        const float *__restrict__ p1 = p0 + pitch;
-                        float *__restrict__ o = op + (r * o_row + x);
+                        const T *__restrict__ p0 = bp + (y0 * pitch + x0 * px + base);
+                        const T *__restrict__ p1 = p0 + pitch;
+                        T *__restrict__ o = op + (r * o_row + x);
 #pragma unroll
                         for (int c = 0; c < CS; ++c) {
-                            float acc = ffma(p0[c * plane], nw, 0.f);
-                            acc = ffma(p0[c * plane + px], ne, acc);
-                            acc = ffma(p1[c * plane], sw, acc);
-                            acc = ffma(p1[c * plane + px], se, acc);
-                            o[c * o_ch] = acc;
+                            float acc = ffma(to_acc(p0[c * plane]), nw, 0.f);
+                            acc = ffma(to_acc(p0[c * plane + px]), ne, acc);
+                            acc = ffma(to_acc(p1[c * plane]), sw, acc);
+                            acc = ffma(to_acc(p1[c * plane + px]), se, acc);
+                            o[c * o_ch] = from_acc<T, float>(acc);
                         }
                     }
                 }
             } else {
                 const bool fallback = (info.z & kInfoFallback) != 0;
-                const float *__restrict__ ip = (const float *)in.p + (int64_t)tc.n * in.sN;
+                const T *__restrict__ ip = (const T *)in.p + (int64_t)tc.n * in.sN;
                 const int sH = in.s2, i_ch = in.s1, sW = kCL ? in.s3 : 1;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -201,30 +204,30 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
                         const float iy = src_index<kBorder, kAlign>(gy, g.H, Hf, Hm1);
                         Taps<float> tp4;
                         make_taps(ix, iy, g.H, g.W, tp4);
-                        float *__restrict__ o = op + (r * o_row + x);
+                        T *__restrict__ o = op + (r * o_row + x);
                         if (!fallback) {
-                            const float *__restrict__ p0 = bp + ((tp4.y0 - info.y) * pitch + (tp4.x0 - info.x) * px);
+                            const T *__restrict__ p0 = bp + ((tp4.y0 - info.y) * pitch + (tp4.x0 - info.x) * px);
 #pragma unroll
                             for (int c = 0; c < CS; ++c) {
-                                const float *__restrict__ pc = p0 + c * plane;
+                                const T *__restrict__ pc = p0 + c * plane;
                                 float acc = 0.f;
-                                if (tp4.mask & 1u) acc = ffma(pc[0], tp4.nw, acc);
-                                if (tp4.mask & 2u) acc = ffma(pc[px], tp4.ne, acc);
-                                if (tp4.mask & 4u) acc = ffma(pc[pitch], tp4.sw, acc);
-                                if (tp4.mask & 8u) acc = ffma(pc[pitch + px], tp4.se, acc);
-                                o[c * o_ch] = acc;
+                                if (tp4.mask & 1u) acc = ffma(to_acc(pc[0]), tp4.nw, acc);
+                                if (tp4.mask & 2u) acc = ffma(to_acc(pc[px]), tp4.ne, acc);
+                                if (tp4.mask & 4u) acc = ffma(to_acc(pc[pitch]), tp4.sw, acc);
+                                if (tp4.mask & 8u) acc = ffma(to_acc(pc[pitch + px]), tp4.se, acc);
+                                o[c * o_ch] = from_acc<T, float>(acc);
                             }
                         } else {
-                            const float *__restrict__ p0 = ip + (tp4.y0 * sH + tp4.x0 * sW);
+                            const T *__restrict__ p0 = ip + (tp4.y0 * sH + tp4.x0 * sW);
 #pragma unroll
                             for (int c = 0; c < CS; ++c) {
-                                const float *__restrict__ pc = p0 + c * i_ch;
+                                const T *__restrict__ pc = p0 + c * i_ch;
                                 float acc = 0.f;
-                                if (tp4.mask & 1u) acc = ffma(__ldg(pc), tp4.nw, acc);
-                                if (tp4.mask & 2u) acc = ffma(__ldg(pc + sW), tp4.ne, acc);
-                                if (tp4.mask & 4u) acc = ffma(__ldg(pc + sH), tp4.sw, acc);
-                                if (tp4.mask & 8u) acc = ffma(__ldg(pc + sH + sW), tp4.se, acc);
-                                o[c * o_ch] = acc;
+                                if (tp4.mask & 1u) acc = ffma(to_acc(ldg(pc)), tp4.nw, acc);
+                                if (tp4.mask & 2u) acc = ffma(to_acc(ldg(pc + sW)), tp4.ne, acc);
+                                if (tp4.mask & 4u) acc = ffma(to_acc(ldg(pc + sH)), tp4.sw, acc);
+                                if (tp4.mask & 8u) acc = ffma(to_acc(ldg(pc + sH + sW)), tp4.se, acc);
+                                o[c * o_ch] = from_acc<T, float>(acc);
                             }
                         }
                     }
@@ -236,33 +239,41 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
     }
 }
 
-template <int CS, bool kBorder, bool kAlign, bool kInter, bool kCL>
+template <typename T, int CS, bool kBorder, bool kAlign, bool kInter, bool kCL>
 bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, int total, cudaStream_t st)
 {
-    auto kern = fwd_tma_kernel<CS, kBorder, kAlign, kInter, kCL>;
+    auto kern = fwd_tma_kernel<T, CS, kBorder, kAlign, kInter, kCL>;
+    constexpr int kSmem = Smem<CS, (int)sizeof(T)>::kTotal;
     static bool attr_done = false;  // per instantiation
     if (!attr_done) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<CS>::kTotal) != cudaSuccess) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
         attr_done = true;
     }
     const int grid = total < sm_count() ? total : sm_count();
-    kern<<<grid, kThreads, Smem<CS>::kTotal, st>>>(tp, pb.in, pb.out, pb.g, tiles_x, tiles_y, total);
+    kern<<<grid, kThreads, kSmem, st>>>(tp, pb.in, pb.out, pb.g, tiles_x, tiles_y, total);
     note_launch();
-    note_kernel(kCL ? "fwd_tma_cl" : "fwd_tma");
+    note_kernel(kCL ? "fwd_tma_cl" : sizeof(T) == 2 ? "fwd_tma_16" : "fwd_tma");
     return true;
 }
 
-template <int CS, bool kInter, bool kCL>
+template <typename T, int CS, bool kInter, bool kCL>
 bool launch_ba(const TmaParams &tp, const Problem &pb, int tx, int ty, int total, cudaStream_t st)
 {
     const bool border = pb.g.padding == PWS_PAD_BORDER, align = pb.g.align != 0;
-    if (border && align) return launch_k<CS, true, true, kInter, kCL>(tp, pb, tx, ty, total, st);
-    if (border) return launch_k<CS, true, false, kInter, kCL>(tp, pb, tx, ty, total, st);
-    if (align) return launch_k<CS, false, true, kInter, kCL>(tp, pb, tx, ty, total, st);
-    return launch_k<CS, false, false, kInter, kCL>(tp, pb, tx, ty, total, st);
+    if (border && align) return launch_k<T, CS, true, true, kInter, kCL>(tp, pb, tx, ty, total, st);
+    if (border) return launch_k<T, CS, true, false, kInter, kCL>(tp, pb, tx, ty, total, st);
+    if (align) return launch_k<T, CS, false, true, kInter, kCL>(tp, pb, tx, ty, total, st);
+    return launch_k<T, CS, false, false, kInter, kCL>(tp, pb, tx, ty, total, st);
+}
+
+template <typename T>
+bool launch_c(const TmaParams &tp, const Problem &pb, bool inter, int tx, int ty, int total, cudaStream_t st)
+{
+    if (pb.g.C == 3) return inter ? launch_ba<T, 3, true, false>(tp, pb, tx, ty, total, st) : launch_ba<T, 3, false, false>(tp, pb, tx, ty, total, st);
+    return inter ? launch_ba<T, 1, true, false>(tp, pb, tx, ty, total, st) : launch_ba<T, 1, false, false>(tp, pb, tx, ty, total, st);
 }
 
 }  // namespace
@@ -313,17 +324,21 @@ bool encode_map_tma(const View &grid, const Geometry &g, CUtensorMap *tm, bool *
     return false;
 }
 
-// frame-shaped (W,H,C,N) fp32 tensor map with the given box
-bool encode_frame_tma(const View &v, int W, int H, int C, int N, int bw, int bh, int bc, CUtensorMap *tm)
+// frame-shaped (W,H,C,N) tensor map with the given box; fp32 or 16-bit float elements
+bool encode_frame_tma(const View &v, int W, int H, int C, int N, int bw, int bh, int bc, CUtensorMap *tm, int dtype)
 {
+    const int eb = dtype == PWS_F32 ? 4 : 2, al = 16 / eb;  // element bytes, elements per 16 bytes
+    if (dtype != PWS_F32 && dtype != PWS_F16 && dtype != PWS_BF16) return false;
     if (reinterpret_cast<uintptr_t>(v.p) & 15) return false;
-    if (v.s3 != 1 || (v.s2 % 4) || (v.s1 % 4) || (v.sN % 4)) return false;
+    if (v.s3 != 1 || (v.s2 % al) || (v.s1 % al) || (v.sN % al) || (bw % al)) return false;
     const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N};
     const uint64_t s1 = C > 1 ? (uint64_t)v.s1 : (uint64_t)v.s2 * H;
     const uint64_t sN = N > 1 ? (uint64_t)v.sN : s1 * C;
     const uint64_t strides[3] = {(uint64_t)v.s2, s1, sN};
     const uint32_t box[4] = {(uint32_t)bw, (uint32_t)bh, (uint32_t)bc, 1};
-    return tma::encode_f32(tm, v.p, 4, dims, strides, box);
+    const CUtensorMapDataType dt = dtype == PWS_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == PWS_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    return tma::encode_elems(tm, dt, eb, v.p, 4, dims, strides, box);
 }
 
 // channels-last frame (element strides s1 == 1, s3 == C): (C*W, H, N) fp32 tensor map, box (C*bw, bh, 1)
@@ -343,7 +358,8 @@ bool launch_forward_tma(const Problem &pb, cudaStream_t st)
 {
     const Geometry &g = pb.g;
     if (tma_disabled()) return false;
-    if (pb.in_dtype != PWS_F32 || pb.grid_dtype != PWS_F32) return false;
+    if (pb.grid_dtype != PWS_F32) return false;
+    if (pb.in_dtype != PWS_F32 && pb.in_dtype != PWS_F16 && pb.in_dtype != PWS_BF16) return false;
     if (g.C != 1 && g.C != 3) return false;
     if (pb.out.s3 != 1) return false;
     if (g.W > (1 << 22) || g.H > (1 << 22)) return false;  // floor_small
@@ -353,15 +369,20 @@ bool launch_forward_tma(const Problem &pb, cudaStream_t st)
     TmaParams tp;
     bool inter = false;
     if (!encode_map_tma(pb.grid, g, &tp.map, &inter)) return false;
+    if (pb.in_dtype != PWS_F32) {  // 16-bit frames (BASELINE config 5: 4K bf16 frames, fp32 maps)
+        for (int s = 0; s < kNumShapes; ++s)
+            if (!encode_frame_tma(pb.in, g.W, g.H, g.C, g.N, box_w(s), box_h(s), g.C, &tp.box[s], pb.in_dtype)) return false;
+        return pb.in_dtype == PWS_F16 ? launch_c<__half>(tp, pb, inter, tiles_x, tiles_y, (int)total, st)
+                                      : launch_c<__nv_bfloat16>(tp, pb, inter, tiles_x, tiles_y, (int)total, st);
+    }
     if (g.C == 3 && pb.in.s1 == 1 && pb.in.s3 == 3) {  // channels-last RGB (the inference site)
         for (int s = 0; s < kNumShapes; ++s)
             if (!encode_frame_cl_tma(pb.in, g.W, g.H, g.C, g.N, box_w_of<true>(s), box_h(s), &tp.box[s])) return false;
-        return inter ? launch_ba<3, true, true>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<3, false, true>(tp, pb, tiles_x, tiles_y, (int)total, st);
+        return inter ? launch_ba<float, 3, true, true>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<float, 3, false, true>(tp, pb, tiles_x, tiles_y, (int)total, st);
     }
     for (int s = 0; s < kNumShapes; ++s)
         if (!encode_frame_tma(pb.in, g.W, g.H, g.C, g.N, box_w(s), box_h(s), g.C, &tp.box[s])) return false;
-    if (g.C == 3) return inter ? launch_ba<3, true, false>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<3, false, false>(tp, pb, tiles_x, tiles_y, (int)total, st);
-    return inter ? launch_ba<1, true, false>(tp, pb, tiles_x, tiles_y, (int)total, st) : launch_ba<1, false, false>(tp, pb, tiles_x, tiles_y, (int)total, st);
+    return launch_c<float>(tp, pb, inter, tiles_x, tiles_y, (int)total, st);
 }
 
 }  // namespace pws

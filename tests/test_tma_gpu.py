@@ -182,3 +182,23 @@ def test_tma_forward_channels_last_frames(pw, shape, pad):
                 assert out.is_contiguous()
                 ref = torch.ops.aten.grid_sampler_2d(frames, g, 0, PAD[pad], align)
                 assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+def test_tma_forward_16bit_frames_fp32_maps(pw, dtype, pad):
+    # BASELINE config 5: bf16 frames with fp32 maps.  Semantics of every 16-bit kernel of this library: taps upcast to
+    # fp32, ATen's fp32 arithmetic, one rounding of the result -- so the expectation is ATen on the upcast frame, rounded
+    for shape in [(2, 3, 64, 64, 64, 64), (3, 1, 100, 128, 100, 128), (2, 3, 48, 200, 40, 136), (1, 3, 270, 480, 270, 480),
+                  (1, 3, 2160, 3840, 2160, 3840)]:
+        N, C, H, W, Ho, Wo = shape
+        for kind in ("smooth", "random", "noisy") if H < 1000 else ("smooth",):
+            for align in (False, True):
+                for layout in ("planar", "interleaved"):
+                    frames, g, _ = make(kind, N, C, H, W, Ho, Wo, align, layout)
+                    f16 = frames.to(dtype)
+                    out = pw.warp2d_forward(f16, g, PAD[pad], align)
+                    assert last_kernel() == "fwd_tma_16"
+                    assert out.dtype == dtype
+                    ref = torch.ops.aten.grid_sampler_2d(f16.float(), g, 0, PAD[pad], align).to(dtype)
+                    assert torch.equal(out, ref)
