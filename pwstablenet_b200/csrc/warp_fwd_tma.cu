@@ -32,7 +32,7 @@ namespace {
 constexpr int kScouts = 2, kGroups = 2, kGroupWarps = 8, kConsumers = kGroups * kGroupWarps;
 constexpr int kThreads = (1 + kScouts + kConsumers) * 32;
 #ifndef PWS_FWD_MAP_STAGES
-#define PWS_FWD_MAP_STAGES 6
+#define PWS_FWD_MAP_STAGES 8
 #endif
 #ifndef PWS_FWD_BOX_STAGES
 #define PWS_FWD_BOX_STAGES 4
