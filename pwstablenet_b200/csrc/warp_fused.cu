@@ -178,6 +178,7 @@ void launch_io(const View &in, const MapSpec &m, const View &out, const Geometry
     if (g.C == 3) { fwd_fused_kernel<TI, TO, 3><<<blocks, kThreads, 0, st>>>(in, m, out, g); note_launch(); }
     else if (g.C == 1) { fwd_fused_kernel<TI, TO, 1><<<blocks, kThreads, 0, st>>>(in, m, out, g); note_launch(); }
     else { fwd_fused_kernel<TI, TO, 0><<<blocks, kThreads, 0, st>>>(in, m, out, g); note_launch(); }
+    note_kernel("fwd_fused");
 }
 
 }  // namespace
@@ -204,6 +205,7 @@ int launch_compose_map(const MapSpec &m, const View &out, int N, int Ho, int Wo,
     if (blocks > INT_MAX) { set_error("compose_map: too many pixels"); return PWS_EUNSUPPORTED; }
     compose_map_kernel<<<(unsigned)blocks, 256, 0, st>>>(m, out, N, Ho, Wo);
     note_launch();
+    note_kernel("compose_map");
     return PWS_OK;
 }
 
