@@ -56,6 +56,8 @@ __device__ unsigned int g_exit_count[kSyncSlots];
 // per cent: distance to the L2 slices, neighbours on the same TPC), and with a static round-robin every frame ended
 // with the fast CTAs waiting at the zero-fill counter of the next frame for the slow ones.
 __device__ unsigned int g_tile_next[kSyncSlots];
+// one slot sequence for every instantiation of the kernel: they all share the counters above
+std::atomic<unsigned> g_next_slot{0};
 
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
 {
@@ -631,7 +633,6 @@ int zero_ahead()
 template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, int total, int n0, cudaStream_t st)
 {
-    static std::atomic<unsigned> next_slot{0};
     auto kern = bwd_tma_kernel<CS, kBorder, kAlign, kInter, kGin, kGgrid>;
     using S = Smem<CS, kGgrid>;
     static bool attr_done = false;  // per instantiation
@@ -644,7 +645,7 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
     }
     const int grid = total < sm_count() ? total : sm_count();
     const int n_frames = total / (tiles_x * tiles_y);
-    const int slot = (int)(next_slot.fetch_add(1u, std::memory_order_relaxed) % kSyncSlots);
+    const int slot = (int)(g_next_slot.fetch_add(1u, std::memory_order_relaxed) % kSyncSlots);
     kern<<<grid, kThreads, S::kTotal, st>>>(tp, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0, n_frames, slot, zero_ahead());
     note_launch();
     note_kernel("bwd_tma");

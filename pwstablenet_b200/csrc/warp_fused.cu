@@ -39,7 +39,13 @@ __device__ __forceinline__ void lattice_map(const MapSpec &m, int n, int i, int 
     float dx = 0.f, dy = 0.f;
     if (m.drift.p) {
         const float *d = (const float *)m.drift.p + (int64_t)n * m.drift.sN + i * m.drift.s1 + j * m.drift.s2;
-        dx = __ldg(d); dy = __ldg(d + m.drift.s3);
+        // interleaved (x,y) pairs -- the lattice the host side composes -- come as one 8-byte load
+        if (m.drift.s3 == 1 && !((reinterpret_cast<uintptr_t>(m.drift.p) & 7) | ((m.drift.sN | m.drift.s1 | m.drift.s2) & 1))) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(d));
+            dx = v.x; dy = v.y;
+        } else {
+            dx = __ldg(d); dy = __ldg(d + m.drift.s3);
+        }
     }
     if (m.base == PWS_BASE_NONE) { mx = dx; my = dy; return; }
     const float bx = lattice_base(j, m.mw, m.base, m.base_align), by = lattice_base(i, m.mh, m.base, m.base_align);
@@ -65,12 +71,9 @@ __device__ __forceinline__ UpCoef up_coef(int dst, int src_size, float scale, bo
     return c;
 }
 
-// the map the sampler sees at output pixel (h, w)
-__device__ __forceinline__ void map_at(const MapSpec &m, int n, int h, int w, float rh, float rw, float &gx, float &gy)
+// the upsampled map from the row / column coefficients of an output pixel
+__device__ __forceinline__ void map_up(const MapSpec &m, int n, const UpCoef &cy, const UpCoef &cx, float &gx, float &gy)
 {
-    if (m.upsample == PWS_UP_NONE) { lattice_map(m, n, h, w, gx, gy); return; }
-    const bool al = m.upsample == PWS_UP_ALIGNED;
-    const UpCoef cy = up_coef(h, m.mh, rh, al), cx = up_coef(w, m.mw, rw, al);
     float x00, y00, x01, y01, x10, y10, x11, y11;
     lattice_map(m, n, cy.i0, cx.i0, x00, y00);
     lattice_map(m, n, cy.i0, cx.i0 + cx.ip, x01, y01);
@@ -79,6 +82,14 @@ __device__ __forceinline__ void map_at(const MapSpec &m, int n, int h, int w, fl
     // h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11), contracted as nvcc contracts ATen's expression
     gx = __fmaf_rn(cy.l0, __fmaf_rn(cx.l0, x00, __fmul_rn(cx.l1, x01)), __fmul_rn(cy.l1, __fmaf_rn(cx.l0, x10, __fmul_rn(cx.l1, x11))));
     gy = __fmaf_rn(cy.l0, __fmaf_rn(cx.l0, y00, __fmul_rn(cx.l1, y01)), __fmul_rn(cy.l1, __fmaf_rn(cx.l0, y10, __fmul_rn(cx.l1, y11))));
+}
+
+// the map the sampler sees at output pixel (h, w)
+__device__ __forceinline__ void map_at(const MapSpec &m, int n, int h, int w, float rh, float rw, float &gx, float &gy)
+{
+    if (m.upsample == PWS_UP_NONE) { lattice_map(m, n, h, w, gx, gy); return; }
+    const bool al = m.upsample == PWS_UP_ALIGNED;
+    map_up(m, n, up_coef(h, m.mh, rh, al), up_coef(w, m.mw, rw, al), gx, gy);
 }
 
 __device__ __forceinline__ void up_scales(const MapSpec &m, int Ho, int Wo, float &rh, float &rw)
@@ -115,14 +126,28 @@ fwd_fused_kernel(const View in, const MapSpec m, const View out, const Geometry 
     up_scales(m, g.Ho, g.Wo, rh, rw);
 
     float gx[2][2], gy[2][2];
+    if (m.upsample == PWS_UP_NONE) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int w = blockIdx.x * kTileW + lane + 32 * i, h = blockIdx.y * kTileH + wrp + 8 * j;
-            gx[j][i] = 0.f; gy[j][i] = 0.f;
-            if (w < g.Wo && h < g.Ho) map_at(m, n, h, w, rh, rw, gx[j][i], gy[j][i]);
-        }
+            for (int i = 0; i < 2; ++i) {
+                const int w = blockIdx.x * kTileW + lane + 32 * i, h = blockIdx.y * kTileH + wrp + 8 * j;
+                gx[j][i] = 0.f; gy[j][i] = 0.f;
+                if (w < g.Wo && h < g.Ho) lattice_map(m, n, h, w, gx[j][i], gy[j][i]);
+            }
+    } else {
+        // a thread's four pixels share two rows and two columns: two row and two column coefficient sets
+        const bool al = m.upsample == PWS_UP_ALIGNED;
+        UpCoef cy[2], cx[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) cy[j] = up_coef(min(blockIdx.y * kTileH + wrp + 8 * j, g.Ho - 1), m.mh, rh, al);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) cx[i] = up_coef(min(blockIdx.x * kTileW + lane + 32 * i, g.Wo - 1), m.mw, rw, al);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) map_up(m, n, cy[j], cx[i], gx[j][i], gy[j][i]);
+    }
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll

@@ -21,6 +21,7 @@
 // on consecutive pixels are 3 words apart (no bank conflict) -- and the output stays dense NCHW like ATen's.
 #include "pws_pipe.cuh"
 
+#include <atomic>
 #include <cstdlib>
 
 namespace pws {
@@ -38,6 +39,16 @@ constexpr int kThreads = (1 + kScouts + kConsumers) * 32;
 #define PWS_FWD_BOX_STAGES 4
 #endif
 constexpr int kMapStages = PWS_FWD_MAP_STAGES, kBoxStages = PWS_FWD_BOX_STAGES;
+constexpr int kInfoStop = 1 << 11;  // info.z: no more tiles for this consumer group
+static_assert(kScouts == kGroups, "scout w feeds consumer group w (and tells it when the tiles have run out)");
+
+// Tiles are handed out dynamically, as in the backward (warp_bwd_tma.cu): the producer takes the next tile index from a
+// per-launch counter and passes it on through shared memory.  A launch owns one slot; the last CTA to leave resets it.
+constexpr int kSlots = 64;
+__device__ unsigned int g_tile_next[kSlots];
+__device__ unsigned int g_exit_count[kSlots];
+// one slot sequence for every instantiation of the kernel: they all share the counters above
+std::atomic<unsigned> g_next_slot{0};
 
 template <int CS, int kElem = 4> struct Smem {
     static constexpr int kBoxBytes = (kMaxBW * kMaxBH * CS * kElem + 127) / 128 * 128;
@@ -45,7 +56,8 @@ template <int CS, int kElem = 4> struct Smem {
     static constexpr int kBoxOff = kMapStages * kMapTileBytes;
     static constexpr int kInfoOff = kBoxOff + kBoxStages * kBoxBytes;
     static constexpr int kBarOff = kInfoOff + kBoxStages * 32;
-    static constexpr int kTotal = kBarOff + (2 * kMapStages + 2 * kBoxStages) * 8;
+    static constexpr int kTileOff = kBarOff + (2 * kMapStages + 2 * kBoxStages) * 8;  // tile index of each map stage
+    static constexpr int kTotal = kTileOff + kMapStages * 4;
     static_assert(kBoxBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
     static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
@@ -60,7 +72,7 @@ struct TmaParams {
 template <typename T, int CS, bool kBorder, bool kAlign, bool kInter, bool kCL>
 __global__ void __launch_bounds__(kThreads, 1)
 fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View out, const Geometry g,
-               const int tiles_x, const int tiles_y, const int total_tiles)
+               const int tiles_x, const int tiles_y, const int total_tiles, const int slot)
 {
     using S = Smem<CS, (int)sizeof(T)>;
     constexpr int kXAlign = 16 / (int)sizeof(T);
@@ -72,6 +84,7 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
     uint64_t *const map_empty = map_full + kMapStages;
     uint64_t *const box_full = map_empty + kMapStages;
     uint64_t *const box_empty = box_full + kBoxStages;
+    volatile int *const s_tile = reinterpret_cast<volatile int *>(smem + S::kTileOff);
 
     // Roles are numbered from the TOP warp of the CTA down: the scheduler favours the higher warp ids when several
     // warps are ready, and the producer and the scouts -- a handful of instructions per tile, but every consumer
@@ -88,33 +101,46 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
     __syncthreads();
 
     if (warp == 0) {
-        // ===== producer: warp map tiles =====
+        // ===== producer: fetches tile indices (the first per CTA is static, the rest come from the launch's counter, one
+        // fetch ahead) and streams the tiles' warp maps; a negative index tells a scout that the tiles have run out =====
         if (lane == 0) {
             tma::prefetch_desc(&tp.map);
-            int it = 0;
-            TileWalk tw;
-            tw.init(blockIdx.x, gridDim.x, tiles_x, tiles_y);
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it, tw.next(tiles_x, tiles_y)) {
+            int t = blockIdx.x;
+            int t_next = (int)atomicAdd(&g_tile_next[slot], 1u) + (int)gridDim.x;
+            int stops = 0;
+            for (int it = 0; stops < kScouts; ++it) {
                 const int s = it % kMapStages, ph = (it / kMapStages) & 1;
                 tma::mbar_wait_relaxed(map_empty + s, ph ^ 1);
-                const TileCoord tc = tw.coord();
+                if (t >= total_tiles) {
+                    s_tile[s] = -1;
+                    tma::mbar_arrive(map_full + s);
+                    ++stops;
+                    continue;
+                }
+                const int t_new = (int)atomicAdd(&g_tile_next[slot], 1u) + (int)gridDim.x;
+                const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
+                s_tile[s] = t;
                 tma::mbar_arrive_expect_tx(map_full + s, kMapTileBytes);
                 if (kInter) tma::load_3d(s_map + s * kMapTileFloats, &tp.map, map_full + s, 2 * tc.w0, tc.h0, tc.n);
                 else tma::load_4d(s_map + s * kMapTileFloats, &tp.map, map_full + s, tc.w0, tc.h0, 0, tc.n);
+                t = t_next; t_next = t_new;
             }
         }
     } else if (warp <= kScouts) {
         // ===== scouts (alternate tiles): map tile -> tap bounding box -> frame box load =====
         if (lane == 0) { tma::prefetch_desc(&tp.box[0]); tma::prefetch_desc(&tp.box[1]); tma::prefetch_desc(&tp.box[2]); }
-        int it = warp - 1;
-        TileWalk tw;
-        tw.init(blockIdx.x + (warp - 1) * gridDim.x, kScouts * gridDim.x, tiles_x, tiles_y);
-        for (int t = blockIdx.x + (warp - 1) * gridDim.x; t < total_tiles; t += kScouts * gridDim.x, it += kScouts, tw.next(tiles_x, tiles_y)) {
+        for (int it = warp - 1;; it += kScouts) {
             const int ms = it % kMapStages, mph = (it / kMapStages) & 1;
             const int bs = it % kBoxStages, bph = (it / kBoxStages) & 1;
-            const TileCoord tc = tw.coord();
-            const int cols = min(kTW, g.Wo - tc.w0), rows = min(kTH, g.Ho - tc.h0);
             tma::mbar_wait_relaxed(map_full + ms, mph);
+            const int t = s_tile[ms];
+            if (t < 0) {
+                tma::mbar_wait_relaxed(box_empty + bs, bph ^ 1);
+                if (lane == 0) { s_info[2 * bs] = make_int4(0, 0, kInfoStop, 0); tma::mbar_arrive(box_full + bs); }
+                break;
+            }
+            const TileCoord tc = tile_coord(t, tiles_x, tiles_xy);
+            const int cols = min(kTW, g.Wo - tc.w0), rows = min(kTH, g.Ho - tc.h0);
             float xlo, xhi, ylo, yhi;
             map_tile_range<kInter>(s_map + ms * kMapTileFloats, rows, cols, lane, xlo, xhi, ylo, yhi);
             tma::mbar_wait_relaxed(box_empty + bs, bph ^ 1);
@@ -136,15 +162,16 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
     } else {
         // ===== consumers =====
         const int cw = warp - 1 - kScouts, grp = cw / kGroupWarps, wg = cw % kGroupWarps;
-        int it = grp;
-        for (int t = blockIdx.x + grp * gridDim.x; t < total_tiles; t += kGroups * gridDim.x, it += kGroups) {
-            const int ms = it % kMapStages, mph = (it / kMapStages) & 1;
+        for (int it = grp;; it += kGroups) {
+            const int ms = it % kMapStages;
             const int bs = it % kBoxStages, bph = (it / kBoxStages) & 1;
-            // one warp of the group polls the mbarriers, the others park on a hardware barrier (no spin)
-            if (wg == 0) { tma::mbar_wait(map_full + ms, mph); tma::mbar_wait(box_full + bs, bph); }
+            // one warp of the group polls the mbarrier, the others park on a hardware barrier (no spin); the scout has
+            // seen the map tile before it loaded the box, so the box barrier covers both
+            if (wg == 0) tma::mbar_wait(box_full + bs, bph);
             tma::named_bar_sync(1 + grp, kGroupWarps * 32);
             const float *mp = s_map + ms * kMapTileFloats;
             const int4 info = s_info[2 * bs], where = s_info[2 * bs + 1];
+            if (info.z & kInfoStop) break;
             TileCoord tc;
             tc.n = info.w; tc.h0 = where.x; tc.w0 = where.y;
             const int shape = info.z & 0xff;
@@ -237,6 +264,16 @@ fwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View o
             if (lane == 0) { tma::mbar_arrive(map_empty + ms); tma::mbar_arrive(box_empty + bs); }
         }
     }
+    __syncthreads();
+    // the last CTA to leave hands the counter slot back clean
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&g_exit_count[slot], 1u) == gridDim.x - 1) {
+            g_tile_next[slot] = 0u;
+            g_exit_count[slot] = 0u;
+            __threadfence();
+        }
+    }
 }
 
 template <typename T, int CS, bool kBorder, bool kAlign, bool kInter, bool kCL>
@@ -253,7 +290,8 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
         attr_done = true;
     }
     const int grid = total < sm_count() ? total : sm_count();
-    kern<<<grid, kThreads, kSmem, st>>>(tp, pb.in, pb.out, pb.g, tiles_x, tiles_y, total);
+    const int slot = (int)(g_next_slot.fetch_add(1u, std::memory_order_relaxed) % kSlots);
+    kern<<<grid, kThreads, kSmem, st>>>(tp, pb.in, pb.out, pb.g, tiles_x, tiles_y, total, slot);
     note_launch();
     note_kernel(kCL ? "fwd_tma_cl" : sizeof(T) == 2 ? "fwd_tma_16" : "fwd_tma");
     return true;
