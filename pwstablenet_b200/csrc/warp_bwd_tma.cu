@@ -59,6 +59,14 @@ __device__ unsigned int g_tile_next[kSyncSlots];
 // one slot sequence for every instantiation of the kernel: they all share the counters above
 std::atomic<unsigned> g_next_slot{0};
 
+// the scouts' progress words: a flag polled by the zero-fill warp, not data
+#ifdef PWS_BWD_ATOMIC_PROGRESS   // shared-memory atomics: silences compute-sanitizer's racecheck (used for the sanitizer runs)
+__device__ __forceinline__ void progress_store(int *p, int v) { atomicExch(p, v); }
+__device__ __forceinline__ int progress_load(int *p) { return atomicOr(p, 0); }
+#else
+__device__ __forceinline__ void progress_store(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+__device__ __forceinline__ int progress_load(int *p) { return *reinterpret_cast<volatile int *>(p); }
+#endif
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p)
 {
     unsigned int v;
@@ -346,7 +354,10 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     uint64_t *const empty = full + kStages;
     uint64_t *const map_full = empty + kStages;
     uint64_t *const map_empty = map_full + kMapStages;
-    volatile int *const s_progress = reinterpret_cast<volatile int *>(smem + S::kProgressOff);  // per scout: how far it has dispatched, in eighths of a frame
+    // per scout: how far it has dispatched, in eighths of a frame.  Written by the scouts and polled by the zero-fill
+    // warp (volatile; compute-sanitizer's racecheck flags exactly this pair and nothing else -- build with
+    // -DPWS_BWD_ATOMIC_PROGRESS to run it clean)
+    int *const s_progress = reinterpret_cast<int *>(smem + S::kProgressOff);
 
     // Roles are numbered from the TOP warp of the CTA down (the scheduler favours the higher warp ids when several
     // warps are ready; the scouts are a handful of instructions per tile, but every consumer waits on them).
@@ -411,7 +422,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 if (lane == 0) {
                     s_info[2 * st] = make_int4(0, 0, kInfoStop, 0);
                     tma::mbar_arrive(full + st); tma::mbar_arrive(full + st);
-                    s_progress[warp] = INT_MAX - 4;  // out of tiles: let the zero-fill warp run to the end
+                    progress_store(&s_progress[warp], INT_MAX - 4);  // out of tiles: let the zero-fill warp run to the end
                 }
                 break;
             }
@@ -458,7 +469,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 q3 = clock64();
 #endif
                 if (kGin) {
-                    s_progress[warp] = progress;  // the zero-fill warp keeps `zero_ahead` eighths ahead of the scouts
+                    progress_store(&s_progress[warp], progress);  // the zero-fill warp keeps `zero_ahead` eighths ahead of the scouts
                     if (tc.n > zero_seen) {
                         while (ld_acquire(&g_zero_done[slot][tc.n]) < gridDim.x) __nanosleep(64);
                         zero_seen = tc.n;
@@ -494,7 +505,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
 #ifdef PWS_EXP_CLOCKS
                 const long long z0 = clock64();
 #endif
-                while (max(s_progress[0], s_progress[1]) + zero_ahead < 8 * f) __nanosleep(256);
+                while (max(progress_load(&s_progress[0]), progress_load(&s_progress[1])) + zero_ahead < 8 * f) __nanosleep(256);
 #ifdef PWS_EXP_CLOCKS
                 const long long z1 = clock64();
 #endif
