@@ -50,7 +50,11 @@ constexpr int kInfoStop = 1 << 11;  // info.z: no more tiles for this consumer g
 // zeroed lines are still in L2 when the REDs land and no separate memset pass runs ahead of the kernel.
 // A launch owns one slot of per-frame completion counters; the last CTA to leave resets the slot.
 constexpr int kSyncSlots = 64, kSyncFrames = 256;
-__device__ unsigned int g_zero_done[kSyncSlots][kSyncFrames];
+// The zero-fill is tracked in bands of 1/8 frame (rows [ceil(b*H/8), ceil((b+1)*H/8)) of every channel plane): a tile
+// only needs the bands its taps can reach.  (Measured: with band tracking the best look-ahead is still 3-4 bands --
+// 0.593 / 0.482 / 0.469 / 0.468 ms at 1 / 2 / 3 / 4 -- so the finer grain buys robustness, not speed.)
+constexpr int kBands = 8;
+__device__ unsigned int g_zero_done[kSyncSlots][kSyncFrames * kBands];
 __device__ unsigned int g_exit_count[kSyncSlots];
 // Tiles are handed out dynamically: the SMs of a B200 do not run this kernel at the same pace (the spread is several
 // per cent: distance to the L2 slices, neighbours on the same TPC), and with a static round-robin every frame ended
@@ -406,7 +410,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
         };
         TileCoord tc = tile_coord(min(t, total_tiles - 1), tiles_x, tiles_xy);
         if (lane == 0 && t < total_tiles) load_map(warp, tc);  // the ring starts out empty
-        int zero_seen = -1;  // frames [0, zero_seen] are known to be zero-filled by every CTA
+        int zero_seen = -1;  // bands [0, zero_seen] (index = 8 * frame + band) are known to be zero-filled by every CTA
 #ifdef PWS_EXP_CLOCKS
         long long s_range = 0, s_wait = 0, s_issue = 0, s_zero = 0; int s_nowait = 0, s_n = 0;
 #endif
@@ -468,12 +472,19 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
 #ifdef PWS_EXP_CLOCKS
                 q3 = clock64();
 #endif
-                if (kGin) {
-                    progress_store(&s_progress[warp], progress);  // the zero-fill warp keeps `zero_ahead` eighths ahead of the scouts
-                    if (tc.n > zero_seen) {
-                        while (ld_acquire(&g_zero_done[slot][tc.n]) < gridDim.x) __nanosleep(64);
-                        zero_seen = tc.n;
+                if (kGin && !(info.z & kInfoEmpty)) {
+                    // the last band this tile's REDs can land in: the box rows when the taps were bounded, else the whole frame
+                    const int y_hi = (info.z & kInfoFallback) ? g.H - 1 : min(info.y + box_h(shape), g.H) - 1;
+                    const int need = kBands * tc.n + (kBands * y_hi) / g.H;
+                    // the zero-fill warp keeps `zero_ahead` bands ahead of what the scouts publish: the output position of
+                    // the tile, or the band it needs if that is further on (a map that samples far away must not starve)
+                    progress_store(&s_progress[warp], max(progress, need));
+                    if (need > zero_seen) {  // bands complete in order: every CTA fills them in order
+                        while (ld_acquire(&g_zero_done[slot][need]) < gridDim.x) __nanosleep(64);
+                        zero_seen = need;
                     }
+                } else if (kGin) {
+                    progress_store(&s_progress[warp], progress);
                 }
                 // second arrival: passes on (cta scope) the acquire above and this scout's view of the map tile
                 tma::mbar_arrive(full + st);
@@ -493,30 +504,36 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             printf("scout cta %3d w %d: tiles %3d range %8lld wait_empty %8lld (no wait: %3d) issue %8lld zero %8lld\n", blockIdx.x, warp, s_n, s_range, s_wait, s_nowait, s_issue, s_zero);
 #endif
     } else if (warp == kZeroWarp) {
-        // ===== zero-fill of grad_input, frame by frame, this CTA's 1/gridDim share, two frames ahead =====
+        // ===== zero-fill of grad_input, band by band, this CTA's 1/gridDim share of every band, `zero_ahead` bands ahead =====
         if (kGin) {
-            const int64_t frame_vec = (int64_t)gin.sN / 4;  // float4 per frame (host-checked: sN % 4 == 0, base 16-byte aligned)
-            const int64_t share = (frame_vec + gridDim.x - 1) / gridDim.x;
-            const int64_t v0 = (int64_t)blockIdx.x * share, v1 = min(frame_vec, v0 + share);
+            const int64_t plane = (int64_t)g.H * g.W;  // dense NCHW frame (host-checked), W % 4 == 0, base 16-byte aligned
 #ifdef PWS_EXP_CLOCKS
             long long z_trig = 0, z_st = 0, z_fence = 0;
 #endif
-            for (int f = 0; f < n_frames; ++f) {
+            for (int idx = 0; idx < n_frames * kBands; ++idx) {
+                const int f = idx / kBands, b = idx % kBands;
 #ifdef PWS_EXP_CLOCKS
                 const long long z0 = clock64();
 #endif
-                while (max(progress_load(&s_progress[0]), progress_load(&s_progress[1])) + zero_ahead < 8 * f) __nanosleep(256);
+                while (max(progress_load(&s_progress[0]), progress_load(&s_progress[1])) + zero_ahead < idx) __nanosleep(256);
 #ifdef PWS_EXP_CLOCKS
                 const long long z1 = clock64();
 #endif
-                float4 *__restrict__ dst = reinterpret_cast<float4 *>((float *)gin.p + (int64_t)(n_begin + f) * gin.sN);
-                for (int64_t v = v0 + lane; v < v1; v += 32) tma::st_zero_v4_hint(dst + v, pol_zero);
+                const int r0 = (b * g.H + kBands - 1) / kBands, r1 = ((b + 1) * g.H + kBands - 1) / kBands;
+                const int band_vec = (r1 - r0) * (g.W / 4);  // float4 per channel plane
+                const int share = (band_vec + gridDim.x - 1) / gridDim.x;
+                const int v0 = blockIdx.x * share, v1 = min(band_vec, v0 + share);
+                float *const fp = (float *)gin.p + (int64_t)(n_begin + f) * gin.sN + (int64_t)r0 * g.W;
+                for (int c = 0; c < CS; ++c) {
+                    float4 *__restrict__ dst = reinterpret_cast<float4 *>(fp + c * plane);
+                    for (int v = v0 + lane; v < v1; v += 32) tma::st_zero_v4_hint(dst + v, pol_zero);
+                }
 #ifdef PWS_EXP_CLOCKS
                 const long long z2 = clock64();
 #endif
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) atomicAdd(&g_zero_done[slot][f], 1u);
+                if (lane == 0) atomicAdd(&g_zero_done[slot][idx], 1u);
 #ifdef PWS_EXP_CLOCKS
                 z_trig += z1 - z0; z_st += z2 - z1; z_fence += clock64() - z2;
 #endif
@@ -626,7 +643,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(&g_exit_count[slot], 1u) == gridDim.x - 1) {
-            if (kGin) for (int f = 0; f < n_frames; ++f) g_zero_done[slot][f] = 0u;
+            if (kGin) for (int i = 0; i < n_frames * kBands; ++i) g_zero_done[slot][i] = 0u;
             g_tile_next[slot] = 0u;
             g_exit_count[slot] = 0u;
             __threadfence();
@@ -700,7 +717,7 @@ BwdTmaPlan *backward_tma_plan(const Problem &pb)
     if (g.W > (1 << 22) || g.H > (1 << 22)) return nullptr;
     if (pb.want_gin && !(pb.gin.s3 == 1 && pb.gin.s2 == g.W && pb.gin.s1 == g.W * g.H)) return nullptr;
     // in-kernel zero-fill writes float4: frame base and frame stride 16-byte aligned
-    if (pb.want_gin && ((reinterpret_cast<uintptr_t>(pb.gin.p) & 15) || (pb.gin.sN % 4))) return nullptr;
+    if (pb.want_gin && ((reinterpret_cast<uintptr_t>(pb.gin.p) & 15) || (pb.gin.sN % 4) || (g.W % 4))) return nullptr;
     if (pb.want_ggrid) {
         // written with plain stores: planar (two scalars) or interleaved (one float2)
         if (pb.ggrid.s3 == 1 && ((reinterpret_cast<uintptr_t>(pb.ggrid.p) & 7) || (pb.ggrid.sN & 1) || (pb.ggrid.s1 & 1) || (pb.ggrid.s2 & 1)))
