@@ -104,6 +104,19 @@ __device__ __forceinline__ void up_scales(const MapSpec &m, int Ho, int Wo, floa
     }
 }
 
+// host twin (float division is correctly rounded on both sides)
+inline void up_scales_host(const MapSpec &m, int Ho, int Wo, float &rh, float &rw)
+{
+    rh = rw = 0.f;
+    if (m.upsample == PWS_UP_ALIGNED) {
+        rh = Ho > 1 ? (float)(m.mh - 1) / (float)(Ho - 1) : 0.f;
+        rw = Wo > 1 ? (float)(m.mw - 1) / (float)(Wo - 1) : 0.f;
+    } else if (m.upsample == PWS_UP_HALF_PIXEL) {
+        rh = (float)m.mh / (float)Ho;
+        rw = (float)m.mw / (float)Wo;
+    }
+}
+
 template <typename T> __device__ __forceinline__ float load_px(const T *p) { return to_acc(ldg(p)); }
 template <> __device__ __forceinline__ float load_px<uint8_t>(const uint8_t *p) { return (float)__ldg(p); }
 template <typename T> __device__ __forceinline__ void store_px(T *p, float v) { *p = from_acc<T, float>(v); }
@@ -181,6 +194,67 @@ fwd_fused_kernel(const View in, const MapSpec m, const View out, const Geometry 
         }
 }
 
+// The inference site, specialised (R/main_new.py:679-684,697-721): uint8 HWC frame in, uint8 HWC frame out, the map
+// is the bilinear upsample of a dense interleaved low-resolution lattice (what the host side composes once per call).
+// Same arithmetic as the generic kernel above, statement for statement -- only the addressing is compile-time: the
+// generic kernel spends 390 instructions per pixel, most of them on run-time strides and layout checks, and is
+// issue-bound (79 % of the issue slots).
+template <bool kBorder, bool kAlignCorners, bool kUpAligned>
+__global__ void __launch_bounds__(kThreads)
+fwd_fused_u8_kernel(const uint8_t *__restrict__ in, const float2 *__restrict__ lattice, uint8_t *__restrict__ out,
+                    const int H, const int W, const int Ho, const int Wo, const int mh, const int mw, const float rh, const float rw)
+{
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int n = blockIdx.z;
+    const uint8_t *__restrict__ ip = in + (int64_t)n * H * W * 3;
+    uint8_t *__restrict__ op = out + (int64_t)n * Ho * Wo * 3;
+    const float2 *__restrict__ L = lattice + (int64_t)n * mh * mw;
+    const int padding = kBorder ? PWS_PAD_BORDER : PWS_PAD_ZEROS;
+
+    UpCoef cy[2], cx[2];
+    int hh[2], ww[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { hh[j] = blockIdx.y * kTileH + wrp + 8 * j; cy[j] = up_coef(min(hh[j], Ho - 1), mh, rh, kUpAligned); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { ww[i] = blockIdx.x * kTileW + lane + 32 * i; cx[i] = up_coef(min(ww[i], Wo - 1), mw, rw, kUpAligned); }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (!(ww[i] < Wo && hh[j] < Ho)) continue;
+            const float2 *r0 = L + cy[j].i0 * mw + cx[i].i0, *r1 = r0 + cy[j].ip * mw;
+            const float2 v00 = __ldg(r0), v01 = __ldg(r0 + cx[i].ip), v10 = __ldg(r1), v11 = __ldg(r1 + cx[i].ip);
+            // h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11), contracted as in map_up()
+            const float gx = __fmaf_rn(cy[j].l0, __fmaf_rn(cx[i].l0, v00.x, __fmul_rn(cx[i].l1, v01.x)), __fmul_rn(cy[j].l1, __fmaf_rn(cx[i].l0, v10.x, __fmul_rn(cx[i].l1, v11.x))));
+            const float gy = __fmaf_rn(cy[j].l0, __fmaf_rn(cx[i].l0, v00.y, __fmul_rn(cx[i].l1, v01.y)), __fmul_rn(cy[j].l1, __fmaf_rn(cx[i].l0, v10.y, __fmul_rn(cx[i].l1, v11.y))));
+            Taps<float> t;
+            make_taps(source_index(gx, W, padding, kAlignCorners), source_index(gy, H, padding, kAlignCorners), H, W, t);
+            const uint8_t *__restrict__ p0 = ip + ((int64_t)t.y0 * W + t.x0) * 3;
+            const uint8_t *__restrict__ p1 = p0 + W * 3;
+            uint8_t *__restrict__ o = op + ((int64_t)hh[j] * Wo + ww[i]) * 3;
+            if (t.mask == 15u) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float acc = ffma((float)__ldg(p0 + c), t.nw, 0.f);
+                    acc = ffma((float)__ldg(p0 + 3 + c), t.ne, acc);
+                    acc = ffma((float)__ldg(p1 + c), t.sw, acc);
+                    acc = ffma((float)__ldg(p1 + 3 + c), t.se, acc);
+                    store_px(o + c, acc);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float acc = 0.f;
+                    if (t.mask & 1u) acc = ffma((float)__ldg(p0 + c), t.nw, acc);
+                    if (t.mask & 2u) acc = ffma((float)__ldg(p0 + 3 + c), t.ne, acc);
+                    if (t.mask & 4u) acc = ffma((float)__ldg(p1 + c), t.sw, acc);
+                    if (t.mask & 8u) acc = ffma((float)__ldg(p1 + 3 + c), t.se, acc);
+                    store_px(o + c, acc);
+                }
+            }
+        }
+}
+
 __global__ void __launch_bounds__(256)
 compose_map_kernel(const MapSpec m, const View out, const int N, const int Ho, const int Wo)
 {
@@ -212,6 +286,29 @@ int launch_forward_fused(const View &in, int in_dtype, const MapSpec &m, const V
                          const Geometry &g, cudaStream_t st)
 {
     if (g.N > 65535 || (g.Ho + kTileH - 1) / kTileH > 65535) { set_error("fused forward: batch or height too large"); return PWS_EUNSUPPORTED; }
+    // the inference site: dense uint8 HWC in and out, dense interleaved lattice, upsampling, nothing else
+    const bool u8_fast = in_dtype == PWS_U8 && out_dtype == PWS_U8 && g.C == 3 && m.base == PWS_BASE_NONE && m.drift.p &&
+        m.upsample != PWS_UP_NONE && !m.has_pre && !m.has_post &&
+        in.s1 == 1 && in.s3 == 3 && in.s2 == 3 * g.W && (g.N == 1 || in.sN == (int64_t)3 * g.W * g.H) &&
+        out.s1 == 1 && out.s3 == 3 && out.s2 == 3 * g.Wo && (g.N == 1 || out.sN == (int64_t)3 * g.Wo * g.Ho) &&
+        m.drift.s3 == 1 && m.drift.s2 == 2 && m.drift.s1 == 2 * m.mw && (g.N == 1 || m.drift.sN == (int64_t)2 * m.mw * m.mh) &&
+        !(reinterpret_cast<uintptr_t>(m.drift.p) & 7);
+    if (u8_fast) {
+        dim3 blocks((g.Wo + kTileW - 1) / kTileW, (g.Ho + kTileH - 1) / kTileH, g.N);
+        float rh, rw;
+        up_scales_host(m, g.Ho, g.Wo, rh, rw);
+        const uint8_t *ip = (const uint8_t *)in.p;
+        const float2 *lp = (const float2 *)m.drift.p;
+        uint8_t *op = (uint8_t *)out.p;
+        const bool border = g.padding == PWS_PAD_BORDER, al = g.align != 0, upa = m.upsample == PWS_UP_ALIGNED;
+#define PWS_U8(B, A, U) fwd_fused_u8_kernel<B, A, U><<<blocks, kThreads, 0, st>>>(ip, lp, op, g.H, g.W, g.Ho, g.Wo, m.mh, m.mw, rh, rw)
+        if (border) { if (al) { if (upa) PWS_U8(true, true, true); else PWS_U8(true, true, false); } else { if (upa) PWS_U8(true, false, true); else PWS_U8(true, false, false); } }
+        else        { if (al) { if (upa) PWS_U8(false, true, true); else PWS_U8(false, true, false); } else { if (upa) PWS_U8(false, false, true); else PWS_U8(false, false, false); } }
+#undef PWS_U8
+        note_launch();
+        note_kernel("fwd_fused_u8");
+        return PWS_OK;
+    }
     if (in_dtype == PWS_F32 && out_dtype == PWS_F32) launch_io<float, float>(in, m, out, g, st);
     else if (in_dtype == PWS_U8 && out_dtype == PWS_F32) launch_io<uint8_t, float>(in, m, out, g, st);
     else if (in_dtype == PWS_U8 && out_dtype == PWS_U8) launch_io<uint8_t, uint8_t>(in, m, out, g, st);

@@ -148,3 +148,29 @@ def test_fused_errors(pw):
         pw.warp_fused(f, drift=d, base="affine", upsample="aligned", out_size=(8, 8))
     with pytest.raises(NotImplementedError):
         pw.warp_fused(f, drift=d, padding_mode="reflection", upsample="aligned", out_size=(8, 8))
+
+
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+@pytest.mark.parametrize("align", [False, True])
+@pytest.mark.parametrize("upsample", ["aligned", "half_pixel"])
+def test_inference_site_specialised_uint8_kernel_equals_the_generic_one(pw, pad, align, upsample):
+    # dense uint8 HWC in/out + dense lattice take fwd_fused_u8_kernel; the same call with an NCHW-stored frame takes
+    # the generic kernel: identical bytes out, for every padding / align_corners / upsample mode, partial tiles
+    # included; and the truncated fp32 plain sample of the emitted map gives the same bytes again
+    from pwstablenet_b200 import _lib
+    N, H, W = 2, 137, 204
+    rng = np.random.default_rng(5)
+    hwc = torch.from_numpy(rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)).cuda()
+    drift = dev(planar_drift(N, 48, 64, 3, amp=0.05)).permute(0, 2, 3, 1)
+    theta = dev(np.tile(np.array([[[1.02, 0.03, 0.01], [-0.03, 0.98, -0.02]]], np.float32), (N, 1, 1)))
+    kw = dict(drift=drift, base="affine", theta=theta, upsample=upsample, out_size=(H, W), padding_mode=pad,
+              align_corners=align, out_dtype=torch.uint8)
+    fast = pw.warp_fused(hwc.permute(0, 3, 1, 2), out_channels_last=True, **kw)
+    assert _lib.last_kernel() == "fwd_fused_u8"
+    nchw = hwc.permute(0, 3, 1, 2).contiguous()
+    generic = pw.warp_fused(nchw, out_channels_last=False, **kw)
+    assert _lib.last_kernel() == "fwd_fused"
+    assert torch.equal(fast.contiguous(), generic)
+    emitted = pw.compose_map(N, (H, W), drift, "affine", theta, False, upsample)
+    plain = pw.grid_sample(nchw.float(), emitted, "bilinear", pad, align)
+    assert torch.equal(generic, plain.clamp(0, 255).to(torch.uint8))
