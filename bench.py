@@ -44,7 +44,7 @@ import torch
 H, W, C = 1080, 1920, 3
 FRAMES = 16                      # frames per GPU per step
 FWD_BYTES_PX, BWD_BYTES_PX = 32, 52   # algorithmic bytes per output pixel, fp32 C=3
-NCU_BWD_DRAM_BYTES = 1_215_070_000 + 753_519_000   # ncu --set full, 16-frame backward launch: read + write (profiles/r01c_bwd_tma.txt)
+NCU_BWD_DRAM_BYTES = 1_162_755_000 + 616_722_000   # ncu --set full, 16-frame backward launch: read + write (profiles/r01c_bwd_tma.txt)
 WORKLOAD = ("1080p (1920x1080) fp32 RGB bilinear warp, forward + backward (grad to frame and map), "
             f"{FRAMES} frames/GPU/step, zeros padding, align_corners=False, NCHW frames, planar-stored map "
             "= identity + 0.03*tanh(low-pass noise)")
