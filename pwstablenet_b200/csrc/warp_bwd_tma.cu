@@ -2,12 +2,15 @@
 //
 // Autograd of R/main_new.py:106,116 (grad -> map) and :197 (grad -> frame), triggered at :214.
 //
-// Same pipeline as warp_fwd_tma.cu: one persistent CTA per SM walks 64x16 tiles of OUTPUT pixels;
-//   warp 0      producer   streams the tile's warp map and grad_output into shared memory (TMA);
-//   warps 1-2   scouts     (alternate tiles) reduce the map tile to the bounding box of its source taps and
-//                          load that box of the frame -- only when grad_grid is wanted, it is its one use;
-//   warps 3-10  consumers  two groups of warps, each group owning every other tile; inside a tile a
-//                          warp owns a 32-pixel-wide strip of 2*16/warps-per-group rows and marches down it.
+// One persistent CTA per SM (19 warps) works on 64x16 tiles of OUTPUT pixels handed out by a per-launch counter:
+//   warps 0-1   scouts     scout w feeds consumer group w: fetches the tile index, TMA-loads the map of its NEXT tile
+//                          into the map ring, reduces the current tile's map to the bounding box of its source taps,
+//                          waits for the tile's stage of the main ring, TMA-loads grad_output and (only when grad_grid
+//                          is wanted -- it is its one use) that box of the frame, and checks that the bands of
+//                          grad_input the tile scatters into have been zero-filled by every CTA;
+//   warps 2-17  consumers  two groups of warps, each group owning every other tile; inside a tile a warp owns a
+//                          32-pixel-wide strip of 2*16/warps-per-group rows and marches down it;
+//   warp 18     zero-fill  zeroes this CTA's share of grad_input, band by band, a few bands ahead of the scouts.
 // The scatter into grad_input is the marching scheme of warp_bwd_lean.cu: a lane whose right neighbour
 // samples the next source pixel hands its east taps over by shuffle, the south taps ride down the strip
 // in registers, and what is left is ~1 RED.ADD.F32 per source pixel and channel on consecutive addresses.

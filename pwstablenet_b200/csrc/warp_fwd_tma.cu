@@ -3,8 +3,9 @@
 // Call sites: R/main_new.py:106,116 (NCHW fp32 frames, planar-stored maps), :197 (interleaved
 // affine_grid maps), :716 (the same at native video resolution).
 //
-// One persistent CTA per SM walks 64x16 tiles of OUTPUT pixels.  Three roles, mbarrier rings between them:
-//   warp 0  producer  streams the tile's warp map into shared memory (TMA, kMapStages ahead);
+// One persistent CTA per SM works on 64x16 tiles of OUTPUT pixels handed out by a per-launch counter.  Three roles,
+// mbarrier rings between them:
+//   warp 0  producer  fetches tile indices and streams the tiles' warp maps into shared memory (TMA, kMapStages ahead);
 //   warps 1-2 scouts  (alternate tiles) reduce the map tile to the bounding box of the source taps it implies --
 //                     the tile's halo under the map -- picks the smallest of three box shapes that
 //                     holds it and issues the TMA load of that box of the frame (all channels);
@@ -19,6 +20,8 @@
 // kCL: the frame is a channels-last view (R/main_new.py:679-684,716: permute(0,3,1,2) of an HWC buffer).  The
 // box is then a (C*BW) x BH slab of the (C*W, H, N) array -- a pixel's channels sit in consecutive words, lanes
 // on consecutive pixels are 3 words apart (no bank conflict) -- and the output stays dense NCHW like ATen's.
+// T = __half / __nv_bfloat16: 16-bit frames with fp32 maps (BASELINE config 5); the box holds 16-bit elements, taps are
+// upcast, the arithmetic is fp32 and the result is rounded once.
 #include "pws_pipe.cuh"
 
 #include <atomic>
