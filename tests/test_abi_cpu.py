@@ -63,6 +63,17 @@ def test_python_shim_argument_errors_match_torch():
         pw.grid_sample(f, g, align_corners=False)
 
 
+def test_fused_entry_rejects_cpu_tensors_and_bad_modes():
+    # the fused map-composition entry has no CPU path either, and says so before any kernel is involved
+    import pwstablenet_b200 as pw
+    frame = torch.zeros(1, 3, 8, 8)
+    drift = torch.zeros(1, 4, 4, 2)
+    with pytest.raises(RuntimeError, match="4-D CUDA tensor"):
+        pw.warp_fused(frame, drift=drift, base="identity", upsample="aligned", out_size=(8, 8))
+    with pytest.raises(RuntimeError, match="4-D CUDA tensor"):
+        pw.warp_fused(torch.zeros(3, 8, 8), drift=drift)
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from pwstablenet_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
