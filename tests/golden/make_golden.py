@@ -32,6 +32,7 @@ def sha(a: np.ndarray) -> str:
 
 
 def main():
+    only_inference = "--inference-only" in sys.argv   # regenerate inference_site.npz without touching the other files
     warnings.filterwarnings("ignore")
     sys.dont_write_bytecode = True
     sys.argv = ["x"]  # lib/cfg.py parses argv at import (R/lib/cfg.py:43)
@@ -90,7 +91,32 @@ def main():
             gg = mi.grad.contiguous().numpy()  # (1,256,256,2)
             out[key + "_ggrid_sub"] = gg[:, ::8, ::8, :].copy()
             out[key + "_ggrid_abssum"] = np.float64(np.abs(gg.astype(np.float64)).sum())
-    np.savez_compressed(os.path.join(HERE, "config1_netg.npz"), **out)
+    if not only_inference:
+        np.savez_compressed(os.path.join(HERE, "config1_netg.npz"), **out)
+
+    # ------------------------------------------------------------------ inference site (R/main_new.py:679-684,697-721)
+    # cv2-style uint8 HWC frame -> float -> permute view; netG's 256x256 map -> permute -> UpsamplingBilinear2d to the
+    # frame size -> permute -> grid_sample (defaults) -> astype(uint8).  The map is the stage-3 map of the netG run
+    # above (train-mode output; process() runs the same ops on the eval-mode output), once as netG emits it at random
+    # init (degenerate: everything samples the centre) and once with the identity added (what a trained
+    # theta looks like), so that the vector also covers a geometry worth testing.
+    ih, iw = 144, 256
+    irng = np.random.default_rng(716)
+    hwc = irng.integers(0, 256, (ih, iw, 3), dtype=np.uint8)   # regenerated by the tests from the same seed
+    now = torch.from_numpy(hwc.astype(np.float32))[None].permute(0, 3, 1, 2)       # :679-684
+    ident = F.affine_grid(torch.tensor([[[1.0, 0, 0], [0, 1.0, 0]]]), (1, 3, 256, 256), align_corners=False)
+    site = {"frame_sha": sha(hwc)}
+    for name, grid in (("netg", maps[2].detach()), ("netg_plus_identity", (maps[2].detach() + ident))):
+        g = grid.permute(0, 3, 1, 2)                                               # :706
+        grid_resize = torch.nn.UpsamplingBilinear2d(size=(ih, iw))(g).permute(0, 2, 3, 1)   # :708-710
+        fake = F.grid_sample(now, grid_resize)                                     # :716
+        samples = fake[0].numpy().transpose((1, 2, 0))                             # :717-719
+        site[name + "_out_u8"] = np.array(samples.astype(np.uint8))                # :721
+        site[name + "_out_f32_sub"] = fake.numpy()[:, :, ::4, ::4].copy()
+    np.savez_compressed(os.path.join(HERE, "inference_site.npz"), **site)
+    print("inference_site.npz", os.path.getsize(os.path.join(HERE, "inference_site.npz")) // 1024, "KiB")
+    if only_inference:
+        return
 
     # ------------------------------------------------------------------ small KATs (stored in full)
     rng = np.random.default_rng(20261017)

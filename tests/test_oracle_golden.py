@@ -130,3 +130,25 @@ def test_nonfinite_coordinates_follow_cuda_semantics():
     out_b = oracle.forward(inp, grid, "border", True)
     assert np.all(np.isfinite(out_b))
     assert out_b[0, 0, 0, 2] == inp[0, 0, 0, 0]  # (-inf, NaN) -> (0, 0)
+
+
+def test_inference_site_golden_from_the_reference_flow():
+    # tests/golden/inference_site.npz: R/main_new.py:679-684,697-721 replayed on CPU by make_golden.py -- uint8 HWC frame,
+    # netG's 256x256 stage-3 map, UpsamplingBilinear2d to the frame size, grid_sample, astype(uint8).  The oracle's
+    # upsample differs from torch's by a few ulp of the map, which may flip a truncation on an integer boundary.
+    site = np.load(os.path.join(GOLD, "inference_site.npz"))
+    cfg = np.load(os.path.join(GOLD, "config1_netg.npz"))
+    ih, iw = 144, 256
+    hwc = np.random.default_rng(716).integers(0, 256, (ih, iw, 3), dtype=np.uint8)
+    assert hashlib.sha256(np.ascontiguousarray(hwc).tobytes()).hexdigest() == str(site["frame_sha"])
+    frame = np.ascontiguousarray(hwc.astype(np.float32).transpose(2, 0, 1)[None])
+    m2 = cfg["map_planar"][2][None]                                   # (1,2,256,256), as netG stores it
+    ident = oracle.affine_map(np.array([[[1, 0, 0], [0, 1, 0]]], np.float32), 256, 256, None, False).transpose(0, 3, 1, 2)
+    for name, lattice in (("netg", m2), ("netg_plus_identity", m2 + ident)):
+        up = oracle.upsample_map(lattice, ih, iw, align_corners=True)             # (1,2,H,W)
+        out = oracle.forward(frame, np.ascontiguousarray(up.transpose(0, 2, 3, 1)), "zeros", False)
+        want_f = site[name + "_out_f32_sub"]
+        assert np.abs(out[:, :, ::4, ::4] - want_f).max() <= 1e-3, name   # measured: 0 (a map off by k ulp would move the tap by k*ulp*W/2 px)
+        got = out[0].transpose(1, 2, 0).astype(np.uint8)
+        diff = np.abs(got.astype(np.int32) - site[name + "_out_u8"].astype(np.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() < 1e-3, (name, diff.max(), (diff != 0).mean())
