@@ -174,3 +174,24 @@ def test_inference_site_specialised_uint8_kernel_equals_the_generic_one(pw, pad,
     emitted = pw.compose_map(N, (H, W), drift, "affine", theta, False, upsample)
     plain = pw.grid_sample(nchw.float(), emitted, "bilinear", pad, align)
     assert torch.equal(generic, plain.clamp(0, 255).to(torch.uint8))
+
+
+@pytest.mark.skip(reason="written at the end of round 1 after the GPU budget was spent: never run on a GPU yet -- "
+                         "remove this marker, run it, and only then trust it")
+def test_inference_site_golden_uint8_through_the_fused_kernel(pw):
+    # tests/golden/inference_site.npz (the reference flow replayed on CPU, make_golden.py): the specialised uint8 kernel
+    # fed with the same frame and netG's stored stage-3 map must give the golden bytes up to the documented truncation
+    # flips (the kernel's upsample differs from torch's CPU one by a few ulp of the map)
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    site = np.load(os.path.join(gold, "inference_site.npz"))
+    cfg = np.load(os.path.join(gold, "config1_netg.npz"))
+    ih, iw = 144, 256
+    hwc = torch.from_numpy(np.random.default_rng(716).integers(0, 256, (1, ih, iw, 3), dtype=np.uint8)).cuda()
+    m2 = dev(cfg["map_planar"][2][None])                       # (1,2,256,256) planar, as netG stores it
+    theta = dev(np.array([[[1, 0, 0], [0, 1, 0]]], np.float32))
+    for name, kw in (("netg", dict(base="none")), ("netg_plus_identity", dict(base="affine", theta=theta))):
+        out = pw.warp_fused(hwc.permute(0, 3, 1, 2), drift=m2.permute(0, 2, 3, 1), upsample="aligned", out_size=(ih, iw),
+                            out_dtype=torch.uint8, out_channels_last=True, **kw)
+        got = out[0].permute(1, 2, 0).contiguous().cpu().numpy()
+        diff = np.abs(got.astype(np.int32) - site[name + "_out_u8"].astype(np.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() < 1e-3, (name, int(diff.max()), float((diff != 0).mean()))
