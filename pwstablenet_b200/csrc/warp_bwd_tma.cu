@@ -2,15 +2,12 @@
 //
 // Autograd of R/main_new.py:106,116 (grad -> map) and :197 (grad -> frame), triggered at :214.
 //
-// One persistent CTA per SM (19 warps) works on 64x16 tiles of OUTPUT pixels handed out by a per-launch counter:
-//   warps 0-1   scouts     scout w feeds consumer group w: fetches the tile index, TMA-loads the map of its NEXT tile
-//                          into the map ring, reduces the current tile's map to the bounding box of its source taps,
-//                          waits for the tile's stage of the main ring, TMA-loads grad_output and (only when grad_grid
-//                          is wanted -- it is its one use) that box of the frame, and checks that the bands of
-//                          grad_input the tile scatters into have been zero-filled by every CTA;
-//   warps 2-17  consumers  two groups of warps, each group owning every other tile; inside a tile a warp owns a
-//                          32-pixel-wide strip of 2*16/warps-per-group rows and marches down it;
-//   warp 18     zero-fill  zeroes this CTA's share of grad_input, band by band, a few bands ahead of the scouts.
+// Same pipeline as warp_fwd_tma.cu: one persistent CTA per SM walks 64x16 tiles of OUTPUT pixels;
+//   warp 0      producer   streams the tile's warp map and grad_output into shared memory (TMA);
+//   warps 1-2   scouts     (alternate tiles) reduce the map tile to the bounding box of its source taps and
+//                          load that box of the frame -- only when grad_grid is wanted, it is its one use;
+//   warps 3-10  consumers  two groups of warps, each group owning every other tile; inside a tile a
+//                          warp owns a 32-pixel-wide strip of 2*16/warps-per-group rows and marches down it.
 // The scatter into grad_input is the marching scheme of warp_bwd_lean.cu: a lane whose right neighbour
 // samples the next source pixel hands its east taps over by shuffle, the south taps ride down the strip
 // in registers, and what is left is ~1 RED.ADD.F32 per source pixel and channel on consecutive addresses.
@@ -361,7 +358,8 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     uint64_t *const empty = full + kStages;
     uint64_t *const map_full = empty + kStages;
     uint64_t *const map_empty = map_full + kMapStages;
-    // per scout: how far it has dispatched, in eighths of a frame.  Written by the scouts and polled by the zero-fill
+    // [0], [1] per scout: how far it has dispatched, in eighths of a frame; [2]: the last band (8 * frame + band) known
+    // to be zero-filled by every CTA, published by the zero-fill warp.  Written by the scouts and polled by the zero-fill
     // warp (volatile; compute-sanitizer's racecheck flags exactly this pair and nothing else -- build with
     // -DPWS_BWD_ATOMIC_PROGRESS to run it clean)
     int *const s_progress = reinterpret_cast<int *>(smem + S::kProgressOff);
@@ -380,6 +378,9 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
 
     if (threadIdx.x == 0) {
         s_progress[0] = 0; s_progress[1] = 0;
+#ifdef PWS_BWD_PUBLISH
+        s_progress[2] = -1;
+#endif
         // full: the scout arrives twice -- once with the byte count of the TMA loads, once when the tile's frame is known
         // to be zero-filled by every CTA; empty: one arrival per consumer warp of the group
         for (int s = 0; s < kStages; ++s) { tma::mbar_init(full + s, 2); tma::mbar_init(empty + s, kGroupWarps); }
@@ -482,10 +483,19 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                     // the zero-fill warp keeps `zero_ahead` bands ahead of what the scouts publish: the output position of
                     // the tile, or the band it needs if that is further on (a map that samples far away must not starve)
                     progress_store(&s_progress[warp], max(progress, need));
+#ifdef PWS_BWD_PUBLISH   // experiment (tools/exp/README.md): never run on a GPU in this form
+                    if (need > zero_seen) {
+                        // the zero-fill warp of this CTA watches the launch's counters and publishes how far every CTA
+                        // has got: the scouts never poll global memory themselves
+                        while ((zero_seen = progress_load(&s_progress[2])) < need) __nanosleep(64);
+                        __threadfence_block();
+                    }
+#else
                     if (need > zero_seen) {  // bands complete in order: every CTA fills them in order
                         while (ld_acquire(&g_zero_done[slot][need]) < gridDim.x) __nanosleep(64);
                         zero_seen = need;
                     }
+#endif
                 } else if (kGin) {
                     progress_store(&s_progress[warp], progress);
                 }
@@ -513,12 +523,39 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
 #ifdef PWS_EXP_CLOCKS
             long long z_trig = 0, z_st = 0, z_fence = 0;
 #endif
-            for (int idx = 0; idx < n_frames * kBands; ++idx) {
+            const int last = n_frames * kBands - 1;
+#ifdef PWS_BWD_PUBLISH
+            // bands complete in order (every CTA fills them in order), so one acquire load per band tells how far all CTAs
+            // have got; the acquire, the block-scope fences around the shared-memory word and the scouts' mbarrier
+            // arrivals carry the ordering on to the consumers' REDs
+            int pub = -1;
+            auto advance = [&]() {
+                if (lane == 0) {
+                    const int before = pub;
+                    while (pub < last && ld_acquire(&g_zero_done[slot][pub + 1]) >= gridDim.x) ++pub;
+                    if (pub != before) { __threadfence_block(); progress_store(&s_progress[2], pub); }
+                }
+                __syncwarp();
+            };
+#endif
+            for (int idx = 0; idx <= last; ++idx) {
                 const int f = idx / kBands, b = idx % kBands;
 #ifdef PWS_EXP_CLOCKS
                 const long long z0 = clock64();
 #endif
+#ifdef PWS_BWD_PUBLISH
+                // lane 0 decides, the warp follows: the condition reads volatile words, and lanes that left the loop at
+                // different iterations would meet the __syncwarp() inside advance() from different program points
+                for (;;) {
+                    int go_on = 0;
+                    if (lane == 0) go_on = max(progress_load(&s_progress[0]), progress_load(&s_progress[1])) + zero_ahead < idx;
+                    if (!__shfl_sync(0xffffffffu, go_on, 0)) break;
+                    advance();
+                    __nanosleep(256);
+                }
+#else
                 while (max(progress_load(&s_progress[0]), progress_load(&s_progress[1])) + zero_ahead < idx) __nanosleep(256);
+#endif
 #ifdef PWS_EXP_CLOCKS
                 const long long z1 = clock64();
 #endif
@@ -537,10 +574,16 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(&g_zero_done[slot][idx], 1u);
+#ifdef PWS_BWD_PUBLISH
+                advance();
+#endif
 #ifdef PWS_EXP_CLOCKS
                 z_trig += z1 - z0; z_st += z2 - z1; z_fence += clock64() - z2;
 #endif
             }
+#ifdef PWS_BWD_PUBLISH
+            while (__shfl_sync(0xffffffffu, pub, 0) < last) { advance(); __nanosleep(128); }
+#endif
 #ifdef PWS_EXP_CLOCKS
             if (lane == 0 && (blockIdx.x % 49) == 0) printf("zclk cta %3d: trig %8lld store %8lld fence %8lld\n", blockIdx.x, z_trig, z_st, z_fence);
 #endif
@@ -603,6 +646,47 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             for (int k = 0; k < CS; ++k) cy.v[k] = 0.f;
 
             if (info.z & kInfoInterior) {
+#if defined(PWS_BWD_SWP)
+                // software-pipelined rows (experiment): the grad_grid part of row r + 1 -- loads, coordinates, taps, no
+                // branches -- is written ahead of the scatter part of row r, so that the two share a basic block and
+                // the scheduler can fill the scatter's shuffle / vote latencies with it
+                float c_ix, c_iy, c_x0f, c_y0f, c_go[CS]; int c_x0, c_y0;
+                auto load_row = [&](int r, float &ix, float &iy, float &x0f, float &y0f, int &x0, int &y0, float (&go)[CS]) {
+                    float gx, gy;
+                    if (kInter) { const float2 v = *reinterpret_cast<const float2 *>(mp + (row0 + r) * (2 * kTW) + 2 * (col0 + lane)); gx = v.x; gy = v.y; }
+                    else { gx = mp[(row0 + r) * kTW + col0 + lane]; gy = mp[kTW * kTH + (row0 + r) * kTW + col0 + lane]; }
+#pragma unroll
+                    for (int k = 0; k < CS; ++k) go[k] = gop[k * (kTW * kTH) + r * kTW];
+                    ix = unnorm<kAlign>(gx, Wf, Wm1); iy = unnorm<kAlign>(gy, Hf, Hm1);
+                    floor_small(ix, x0f, x0); floor_small(iy, y0f, y0);
+                };
+                load_row(0, c_ix, c_iy, c_x0f, c_y0f, c_x0, c_y0, c_go);
+                if (kGgrid) {
+                    bwd_row<CS, false, true, false, true>(lane, true, 0xffffffffu, c_ix, c_iy, c_x0f, c_y0f, c_x0, c_y0, gxm_in, gym_in, c_go,
+                                                          bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gip0, gs1, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
+                    ggq += ggrid.s1;
+                }
+#pragma unroll
+                for (int r = 0; r < kStripRows; ++r) {
+                    float n_ix = 0.f, n_iy = 0.f, n_x0f = 0.f, n_y0f = 0.f, n_go[CS]; int n_x0 = 0, n_y0 = 0;
+#pragma unroll
+                    for (int k = 0; k < CS; ++k) n_go[k] = 0.f;
+                    if (r + 1 < kStripRows) {
+                        load_row(r + 1, n_ix, n_iy, n_x0f, n_y0f, n_x0, n_y0, n_go);
+                        if (kGgrid) {
+                            bwd_row<CS, false, true, false, true>(lane, true, 0xffffffffu, n_ix, n_iy, n_x0f, n_y0f, n_x0, n_y0, gxm_in, gym_in, n_go,
+                                                                  bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gip0, gs1, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
+                            ggq += ggrid.s1;
+                        }
+                    }
+                    if (kGin)
+                        bwd_row<CS, true, false, false, true>(lane, true, 0xffffffffu, c_ix, c_iy, c_x0f, c_y0f, c_x0, c_y0, gxm_in, gym_in, c_go,
+                                                              bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gip0, gs1, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
+                    c_ix = n_ix; c_iy = n_iy; c_x0f = n_x0f; c_y0f = n_y0f; c_x0 = n_x0; c_y0 = n_y0;
+#pragma unroll
+                    for (int k = 0; k < CS; ++k) c_go[k] = n_go[k];
+                }
+#else
 #pragma unroll kRowUnroll
                 for (int r = 0; r < kStripRows; ++r) {
                     float gx, gy, go[CS];
@@ -617,6 +701,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                                                             bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gip0, gs1, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
                     if (kGgrid) ggq += ggrid.s1;
                 }
+#endif
             } else {
                 masked_strip<CS, kBorder, kAlign, kInter, kGin, kGgrid>(lane, info, h0, w0, row0, col0, mp, gop, bp, pitch, plane, ip, in.s2, in.s1,
                                                                         g, gip0, gs1, ggq, ggrid.s1, ggrid.s3, cy, q, pol_last, pol_gg);
