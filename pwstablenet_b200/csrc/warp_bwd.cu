@@ -198,20 +198,19 @@ namespace {
 
 bool force_generic()
 {
+#ifdef PWS_DEV_HOOKS
     static const bool v = [] { const char *e = std::getenv("PWS_FORCE_DIRECT"); return e && e[0] == '1'; }();
     return v;
+#else
+    return false;
+#endif
 }
 
 int64_t chunk_bytes()
 {
     // grad_input bytes zero-filled ahead of each scatter launch; must stay well inside L2
-    static int64_t v = [] {
-        const char *e = std::getenv("PWS_BWD_CHUNK_MB");
-        int64_t mb = e ? std::atoll(e) : 4096;  // measured: while the kernel is issue-bound one launch beats L2-sized chunks
-        if (mb < 1) mb = 1;
-        return mb << 20;
-    }();
-    return v;
+    // (measured: while the kernel is issue-bound one launch beats L2-sized chunks)
+    return (int64_t)4096 << 20;
 }
 
 template <typename T>

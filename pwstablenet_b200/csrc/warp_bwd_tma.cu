@@ -17,6 +17,8 @@
 // grad_grid is accumulated in ATen's exact statement order from taps read out of the shared-memory box:
 // bit-identical to the other backward kernels; grad_input differs only by atomic order.
 #include "pws_pipe.cuh"
+#include "pws_launch.cuh"
+#include "pws_f32x2.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -28,18 +30,21 @@ using namespace pipe;
 
 namespace {
 
-#ifdef PWS_EXP_NORED   // experiment: drop the scatter's atomics (results are wrong) to time everything else
-#define PWS_RED(p, v) do { if ((v) == 1.2345e-30f) tma::red_add_f32((p), (v)); } while (0)
-#else
 // explicit fire-and-forget reduction: with a fence elsewhere in the kernel nvcc turns atomicAdd into the
 // returning ATOMG form, whose round trip to L2 the scatter would then wait for
 #define PWS_RED(p, v) tma::red_add_f32((p), (v))
-#endif
 
-#ifndef PWS_BWD_UNROLL
-#define PWS_BWD_UNROLL 2
+// Scatter refinements of the interior body (development builds may switch them off to measure their share):
+//   east carry    an east-bottom tap nobody takes over is parked like the south-west sum and merges into the lane's own
+//                 east tap of the next row (one queue entry per broken horizontal chain instead of two);
+//   vertical dup  a row that samples the SAME source row as the one above adds the parked sum to its own bottom sum
+//                 instead of flushing it.
+#ifndef PWS_BWD_ECARRY
+#define PWS_BWD_ECARRY 1
 #endif
-constexpr int kRowUnroll = PWS_BWD_UNROLL;
+#ifndef PWS_BWD_VDUP
+#define PWS_BWD_VDUP 1
+#endif
 constexpr int kScouts = 2, kGroups = 2, kGroupWarps = 8, kConsumers = kGroups * kGroupWarps;
 constexpr int kThreads = (kScouts + kConsumers + 1) * 32;  // scouts, consumers, the warp that zero-fills grad_input
 constexpr int kZeroWarp = kScouts + kConsumers;
@@ -49,7 +54,7 @@ constexpr int kInfoStop = 1 << 11;  // info.z: no more tiles for this consumer g
 // grad_input is zero-filled INSIDE the kernel, one frame at a time, two frames ahead of the scatter: the
 // zeroed lines are still in L2 when the REDs land and no separate memset pass runs ahead of the kernel.
 // A launch owns one slot of per-frame completion counters; the last CTA to leave resets the slot.
-constexpr int kSyncSlots = 64, kSyncFrames = 256;
+constexpr int kSyncSlots = kLaunchSlots, kSyncFrames = 256;
 // The zero-fill is tracked in bands of 1/8 frame (rows [ceil(b*H/8), ceil((b+1)*H/8)) of every channel plane): a tile
 // only needs the bands its taps can reach.  (Measured: with band tracking the best look-ahead is still 3-4 bands --
 // 0.593 / 0.482 / 0.469 / 0.468 ms at 1 / 2 / 3 / 4 -- so the finer grain buys robustness, not speed.)
@@ -60,8 +65,9 @@ __device__ unsigned int g_exit_count[kSyncSlots];
 // per cent: distance to the L2 slices, neighbours on the same TPC), and with a static round-robin every frame ended
 // with the fast CTAs waiting at the zero-fill counter of the next frame for the slow ones.
 __device__ unsigned int g_tile_next[kSyncSlots];
-// one slot sequence for every instantiation of the kernel: they all share the counters above
-std::atomic<unsigned> g_next_slot{0};
+// (slots are leased per device and reused only after their previous launch has finished: pws_launch.cuh)
+// how far the zero-fill runs ahead of the scatter, in eighths of a frame
+constexpr int kZeroAhead = 4;
 
 // the scouts' progress words: a flag polled by the zero-fill warp, not data
 #ifdef PWS_BWD_ATOMIC_PROGRESS   // shared-memory atomics: silences compute-sanitizer's racecheck (used for the sanitizer runs)
@@ -140,63 +146,69 @@ __device__ __forceinline__ void queue_put(Queue<CS> &q, int pos, int off, const 
     if (CS == 3) *reinterpret_cast<int4 *>(q.buf + pos) = make_int4(off, __float_as_int(v[0]), __float_as_int(v[CS > 1 ? 1 : 0]), __float_as_int(v[CS > 2 ? 2 : 0]));
     else *reinterpret_cast<int2 *>(q.buf + pos) = make_int2(off, __float_as_int(v[0]));
 }
+// element `off` of a plane: one IMAD.WIDE (the compiler otherwise widens the offset once and adds it to every plane base
+// with carry chains)
+__device__ __forceinline__ float *at(float *base, int off)
+{
+    float *p;
+    asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(p) : "r"(off), "l"(base));
+    return p;
+}
+
+// gp[k]: this frame's grad_input plane of channel k (one 64-bit base per plane; an entry's offset is 32-bit)
 template <int CS>
-__device__ __forceinline__ void queue_pop_red(const Queue<CS> &q, int pos, float *const gip0, const int64_t gs1, const uint64_t pol_last)
+__device__ __forceinline__ void queue_pop_red(const Queue<CS> &q, int pos, float *const (&gp)[CS])
 {
     if (CS == 3) {
         const int4 e = *reinterpret_cast<const int4 *>(q.buf + pos);
-        float *const p = gip0 + e.x;  // the three channel planes of one source pixel
-        PWS_RED(p, __int_as_float(e.y));
-        PWS_RED(p + gs1, __int_as_float(e.z));
-        PWS_RED(p + 2 * gs1, __int_as_float(e.w));
+        PWS_RED(at(gp[0], e.x), __int_as_float(e.y));
+        PWS_RED(at(gp[CS > 1 ? 1 : 0], e.x), __int_as_float(e.z));
+        PWS_RED(at(gp[CS > 2 ? 2 : 0], e.x), __int_as_float(e.w));
     } else {
         const int2 e = *reinterpret_cast<const int2 *>(q.buf + pos);
-        PWS_RED(gip0 + e.x, __int_as_float(e.y));
+        PWS_RED(at(gp[0], e.x), __int_as_float(e.y));
     }
 }
-// dense 32-lane REDs while at least a warp's worth of entries is queued
+// one dense 32-lane RED per channel once a warp's worth of entries is queued (a push adds at most 32 entries to fewer
+// than 32, so one round always brings the count back below 32)
 template <int CS>
-__device__ __forceinline__ void queue_drain(Queue<CS> &q, float *const gip0, const int64_t gs1, int lane, const uint64_t pol_last)
+__device__ __forceinline__ void queue_drain(Queue<CS> &q, float *const (&gp)[CS], int lane)
 {
     __syncwarp();
-#pragma unroll 1
-    while (q.count >= 32) {
-        queue_pop_red<CS>(q, q.count - 32 + lane, gip0, gs1, pol_last);
+    if (q.count >= 32) {
+        queue_pop_red<CS>(q, q.count - 32 + lane, gp);
         q.count -= 32;
     }
     __syncwarp();
 }
 template <int CS>
-__device__ __forceinline__ void queue_flush(Queue<CS> &q, float *const gip0, const int64_t gs1, int lane, const uint64_t pol_last)
+__device__ __forceinline__ void queue_flush(Queue<CS> &q, float *const (&gp)[CS], int lane)
 {
-    queue_drain<CS>(q, gip0, gs1, lane, pol_last);
-    if (lane < q.count) queue_pop_red<CS>(q, lane, gip0, gs1, pol_last);
+    queue_drain<CS>(q, gp, lane);
+    if (lane < q.count) queue_pop_red<CS>(q, lane, gp);
     q.count = 0;
     __syncwarp();
 }
 
-// One output row (32 pixels) of a warp.  kMasked=false: every lane is a real pixel with 4 valid taps.
-// kBoxTaps: the taps of grad_grid come from the shared-memory box (tap = box[(y - by) * pitch + (x - bx)] per plane).
-template <int CS, bool kGin, bool kGgrid, bool kMasked, bool kBoxTaps>
-__device__ __forceinline__ void bwd_row(
+// One output row (32 pixels) of a warp in a tile that is NOT interior (frame border, partial tile, no box): every tap and
+// every lane is checked.  kBoxTaps: the taps of grad_grid come from the shared-memory box
+// (tap = box[(y - by) * pitch + (x - bx)] per plane), else from global memory.
+template <int CS, bool kGin, bool kGgrid, bool kBoxTaps>
+__device__ __forceinline__ void masked_row(
     const int lane, const bool px_ok, const unsigned live,
     const float ix, const float iy, const float x0f, const float y0f, const int x0, const int y0,
     const float gxm, const float gym, const float (&go)[CS],
     const float *__restrict__ box, const int pitch, const int plane,
     const float *__restrict__ ip, const int sH, const int i_ch, const int H, const int W,
-    float *const gip0, const int64_t gs1,
-    float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy, Queue<CS> &q, const uint64_t pol_last, const uint64_t pol_first)
+    float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy, Queue<CS> &q, const uint64_t pol_first)
 {
     const float dw = fsub(x0f + 1.0f, ix), de = fsub(ix, x0f), dn = fsub(y0f + 1.0f, iy), ds = fsub(iy, y0f);
-    unsigned mask = 15u;
-    if (kMasked) {
-        const bool xw = (unsigned)x0 < (unsigned)W, xe = (unsigned)(x0 + 1) < (unsigned)W;
-        const bool yn = (unsigned)y0 < (unsigned)H, ys = (unsigned)(y0 + 1) < (unsigned)H;
-        mask = ((xw && yn) ? 1u : 0u) | ((xe && yn) ? 2u : 0u) | ((xw && ys) ? 4u : 0u) | ((xe && ys) ? 8u : 0u);
-        if (!px_ok) mask = 0u;
-    }
+    const bool xw = (unsigned)x0 < (unsigned)W, xe = (unsigned)(x0 + 1) < (unsigned)W;
+    const bool yn = (unsigned)y0 < (unsigned)H, ys = (unsigned)(y0 + 1) < (unsigned)H;
+    unsigned mask = ((xw && yn) ? 1u : 0u) | ((xe && yn) ? 2u : 0u) | ((xw && ys) ? 4u : 0u) | ((xe && ys) ? 8u : 0u);
+    if (!px_ok) mask = 0u;
 
-    if (kGgrid && (!kMasked || px_ok)) {
+    if (kGgrid && px_ok) {
         float gix = 0.f, giy = 0.f;
         const float *__restrict__ p0 = kBoxTaps ? box + (y0 * pitch + x0) : ip + (y0 * sH + x0);
         const int row = kBoxTaps ? pitch : sH, ch = kBoxTaps ? plane : i_ch;
@@ -205,21 +217,21 @@ __device__ __forceinline__ void bwd_row(
             const float *__restrict__ pc = p0 + k * ch;
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
             if (kBoxTaps) {
-                if (!kMasked || (mask & 1u)) v0 = pc[0];
-                if (!kMasked || (mask & 2u)) v1 = pc[1];
-                if (!kMasked || (mask & 4u)) v2 = pc[row];
-                if (!kMasked || (mask & 8u)) v3 = pc[row + 1];
+                if (mask & 1u) v0 = pc[0];
+                if (mask & 2u) v1 = pc[1];
+                if (mask & 4u) v2 = pc[row];
+                if (mask & 8u) v3 = pc[row + 1];
             } else {
-                if (!kMasked || (mask & 1u)) v0 = __ldg(pc);
-                if (!kMasked || (mask & 2u)) v1 = __ldg(pc + 1);
-                if (!kMasked || (mask & 4u)) v2 = __ldg(pc + row);
-                if (!kMasked || (mask & 8u)) v3 = __ldg(pc + row + 1);
+                if (mask & 1u) v0 = __ldg(pc);
+                if (mask & 2u) v1 = __ldg(pc + 1);
+                if (mask & 4u) v2 = __ldg(pc + row);
+                if (mask & 8u) v3 = __ldg(pc + row + 1);
             }
             // ATen's statement order: t = v*d rounded, then one fma with gOut
-            if (!kMasked || (mask & 1u)) { gix = ffma(-fmul(v0, dn), go[k], gix); giy = ffma(-fmul(v0, dw), go[k], giy); }
-            if (!kMasked || (mask & 2u)) { gix = ffma(fmul(v1, dn), go[k], gix);  giy = ffma(-fmul(v1, de), go[k], giy); }
-            if (!kMasked || (mask & 4u)) { gix = ffma(-fmul(v2, ds), go[k], gix); giy = ffma(fmul(v2, dw), go[k], giy); }
-            if (!kMasked || (mask & 8u)) { gix = ffma(fmul(v3, ds), go[k], gix);  giy = ffma(fmul(v3, de), go[k], giy); }
+            if (mask & 1u) { gix = ffma(-fmul(v0, dn), go[k], gix); giy = ffma(-fmul(v0, dw), go[k], giy); }
+            if (mask & 2u) { gix = ffma(fmul(v1, dn), go[k], gix);  giy = ffma(-fmul(v1, de), go[k], giy); }
+            if (mask & 4u) { gix = ffma(-fmul(v2, ds), go[k], gix); giy = ffma(fmul(v2, dw), go[k], giy); }
+            if (mask & 8u) { gix = ffma(fmul(v3, ds), go[k], gix);  giy = ffma(fmul(v3, de), go[k], giy); }
         }
         gix = fmul(gxm, gix); giy = fmul(gym, giy);
         tma::st_f32_hint(ggq, gix, pol_first); tma::st_f32_hint(ggq + gg_s3, giy, pol_first);
@@ -228,26 +240,10 @@ __device__ __forceinline__ void bwd_row(
     if (kGin) {
         const float nw = fmul(dw, dn), ne = fmul(de, dn), sw = fmul(dw, ds), se = fmul(de, ds);
         const int o_nw = y0 * W + x0;  // grad_input is dense NCHW
-        bool take, given;
-#ifndef PWS_BWD_SHFL4
-        if (!kMasked) {
-            // every tap is inside the frame, so x0 <= W - 2 and "left neighbour's offset + 1 == mine" can only mean the
-            // same row: one shuffle and one vote instead of four shuffles (lane l gives iff lane l + 1 takes)
-            const int o_left = __shfl_up_sync(0xffffffffu, o_nw, 1);
-            take = lane > 0 && o_left + 1 == o_nw;
-            given = ((__ballot_sync(0xffffffffu, take) >> 1) >> lane) & 1u;
-        } else
-#endif
-        {
-            const int px0 = __shfl_up_sync(0xffffffffu, x0, 1), py0 = __shfl_up_sync(0xffffffffu, y0, 1);
-            const int nx0 = __shfl_down_sync(0xffffffffu, x0, 1), ny0 = __shfl_down_sync(0xffffffffu, y0, 1);
-            take = lane > 0 && px0 + 1 == x0 && py0 == y0;
-            given = lane < 31 && nx0 == x0 + 1 && ny0 == y0;
-            if (kMasked) {
-                take = take && px_ok && ((live >> (lane - 1)) & 1u);
-                given = given && px_ok && ((live >> (lane + 1)) & 1u);
-            }
-        }
+        const int px0 = __shfl_up_sync(0xffffffffu, x0, 1), py0 = __shfl_up_sync(0xffffffffu, y0, 1);
+        const int nx0 = __shfl_down_sync(0xffffffffu, x0, 1), ny0 = __shfl_down_sync(0xffffffffu, y0, 1);
+        const bool take = lane > 0 && px0 + 1 == x0 && py0 == y0 && px_ok && ((live >> (lane - 1)) & 1u);
+        const bool given = lane < 31 && nx0 == x0 + 1 && ny0 == y0 && px_ok && ((live >> (lane + 1)) & 1u);
         const bool chain = cy.live && cy.x == x0 && cy.y == y0;
         const int o_cy = cy.y * W + cy.x;
         // stragglers of this row -> queue: east taps nobody takes over (top and bottom), parked sums whose chain broke
@@ -262,64 +258,47 @@ __device__ __forceinline__ void bwd_row(
             if (take) { top += ptop; bot += pbot; }
             brk[k] = cy.v[k];
             if (chain) top += cy.v[k];
-            if (mask & 1u) PWS_RED(gip0 + o_nw + k * gs1, top);
+            if (mask & 1u) PWS_RED(at(gp[k], o_nw), top);
             cy.v[k] = bot;
         }
-#ifndef PWS_EXP_NOQUEUE   // experiment: drop the stragglers (results are wrong) to time the queue's share of a row
-        if (!kMasked) {
-            // all taps valid: the two east classes share their predicate
-            const unsigned b = __ballot_sync(0xffffffffu, p_e1);
-            if (b) {
-                const int n = __popc(b), rank = __popc(b & lt);
-                if (p_e1) queue_put<CS>(q, q.count + rank, o_nw + 1, etop);
-                q.count += n;
-                if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
-                if (p_e1) queue_put<CS>(q, q.count + rank, o_nw + W + 1, ebot);
-                q.count += n;
-                if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
-            }
-        } else {
-            const unsigned b1 = __ballot_sync(0xffffffffu, p_e1), b2 = __ballot_sync(0xffffffffu, p_e2);
-            if (b1) {
-                if (p_e1) queue_put<CS>(q, q.count + __popc(b1 & lt), o_nw + 1, etop);
-                q.count += __popc(b1);
-                if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
-            }
-            if (b2) {
-                if (p_e2) queue_put<CS>(q, q.count + __popc(b2 & lt), o_nw + W + 1, ebot);
-                q.count += __popc(b2);
-                if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
-            }
+        const unsigned b1 = __ballot_sync(0xffffffffu, p_e1), b2 = __ballot_sync(0xffffffffu, p_e2), b3 = __ballot_sync(0xffffffffu, p_f);
+        if (b1) {
+            if (p_e1) queue_put<CS>(q, q.count + __popc(b1 & lt), o_nw + 1, etop);
+            q.count += __popc(b1);
+            if (q.count >= 32) queue_drain<CS>(q, gp, lane);
         }
-        {
-            const unsigned b = __ballot_sync(0xffffffffu, p_f);
-            if (b) {
-                const int pos = q.count + __popc(b & lt);
-                if (p_f) queue_put<CS>(q, pos, o_cy, brk);
-                q.count += __popc(b);
-                if (q.count >= 32) queue_drain<CS>(q, gip0, gs1, lane, pol_last);
-            }
+        if (b2) {
+            if (p_e2) queue_put<CS>(q, q.count + __popc(b2 & lt), o_nw + W + 1, ebot);
+            q.count += __popc(b2);
+            if (q.count >= 32) queue_drain<CS>(q, gp, lane);
         }
-#endif
+        if (b3) {
+            if (p_f) queue_put<CS>(q, q.count + __popc(b3 & lt), o_cy, brk);
+            q.count += __popc(b3);
+            if (q.count >= 32) queue_drain<CS>(q, gp, lane);
+        }
         cy.x = x0; cy.y = y0 + 1;
         cy.live = (mask & 4u) != 0u;
     }
 }
 
-// A strip of a tile that is not "interior" (frame border, partial tile, fallback): the masked bodies.
+// A strip of a tile that is not "interior": the masked rows, then the parked south-west sums.
 template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 __device__ __forceinline__ void masked_strip(
     const int lane, const int4 info, const int h0, const int w0, const int row0, const int col0,
     const float *__restrict__ mp, const float *__restrict__ gop, const float *__restrict__ bp, const int pitch, const int plane,
     const float *__restrict__ ip, const int sH, const int i_ch, const Geometry g,
-    float *const gip0, const int64_t gs1, float *__restrict__ ggq, const int gg_s1, const int gg_s3, Carry<CS> &cy, Queue<CS> &q,
-    const uint64_t pol_last, const uint64_t pol_first)
+    float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Queue<CS> &q, const uint64_t pol_first)
 {
     const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
     const bool col_ok = w0 + lane < g.Wo;
     const unsigned live = __ballot_sync(0xffffffffu, col_ok);
     const bool box_taps = kGgrid && !(info.z & (kInfoFallback | kInfoEmpty));
     const int rows = min(kStripRows, g.Ho - h0);  // may be <= 0 for the strips below the last row
+    Carry<CS> cy;
+    cy.x = 0; cy.y = 0; cy.live = false;
+#pragma unroll
+    for (int k = 0; k < CS; ++k) cy.v[k] = 0.f;
     for (int r = 0; r < rows; ++r) {
         float gx, gy, go[CS];
         if (kInter) { const float2 v = *reinterpret_cast<const float2 *>(mp + (row0 + r) * (2 * kTW) + 2 * (col0 + lane)); gx = v.x; gy = v.y; }
@@ -332,19 +311,150 @@ __device__ __forceinline__ void masked_strip(
         const float x0f = floorf(ix), y0f = floorf(iy);
         const int x0 = (int)x0f, y0 = (int)y0f;
         if (box_taps)
-            bwd_row<CS, kGin, kGgrid, true, true>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
-                                                   bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gip0, gs1, ggq, gg_s3, cy, q, pol_last, pol_first);
+            masked_row<CS, kGin, kGgrid, true>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
+                                               bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gp, ggq, gg_s3, cy, q, pol_first);
         else
-            bwd_row<CS, kGin, kGgrid, true, false>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
-                                                    bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gip0, gs1, ggq, gg_s3, cy, q, pol_last, pol_first);
+            masked_row<CS, kGin, kGgrid, false>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
+                                                bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gp, ggq, gg_s3, cy, q, pol_first);
         if (kGgrid) ggq += gg_s1;
+    }
+    if (kGin && cy.live) {
+        const int o_cy = cy.y * g.W + cy.x;
+#pragma unroll
+        for (int k = 0; k < CS; ++k) PWS_RED(at(gp[k], o_cy), cy.v[k]);
+    }
+}
+
+// insert one class of stragglers (predicate p, entry (off, v)) into the warp's queue; all 32 lanes call this
+template <int CS>
+__device__ __forceinline__ void queue_push(Queue<CS> &q, const bool p, const int off, const float (&v)[CS], const unsigned lt,
+                                           float *const (&gp)[CS], const int lane)
+{
+    const unsigned b = __ballot_sync(0xffffffffu, p);
+    if (b) {
+        if (p) queue_put<CS>(q, q.count + __popc(b & lt), off, v);
+        q.count += __popc(b);
+        if (q.count >= 32) queue_drain<CS>(q, gp, lane);
+    }
+}
+
+// A strip (32 pixels x kStripRows rows) of an INTERIOR tile: the tile is full and every tap of every pixel lies inside
+// the frame, so there are no masks, the floor is one round-down add (floor_small), and a source pixel is identified by its
+// linear offset alone.  The arithmetic runs on fp32 PAIRS (pws_f32x2.cuh) wherever two independent chains exist:
+//   coordinates  (x, y) through unnormalise / floor / fraction together;
+//   grad_grid    the accumulators (giy, gix) as one pair: per tap and channel one FMUL2 (tap value x the pair of
+//                fraction weights, sign folded into the weights: -(v*d) == v*(-d) exactly) and one FFMA2 with
+//                grad_output -- ATen's statements, operation for operation, so the result is bit-identical;
+//   grad_input   (north, south) weight pairs: (nw, sw) = dw * (dn, ds), (ne, se) = de * (dn, ds), the products with
+//                grad_output and the take-over add as pairs.
+// dw = 1 - de instead of (x0 + 1) - ix: de = ix - x0 is exact (Sterbenz), so both are the rounding of the same real
+// number 1 + x0 - ix.
+// SHAPE: the tile's box shape -- row pitch and plane size of the box are compile-time, the twelve taps of a pixel are
+// one address register plus immediates.
+template <int CS, bool kAlign, bool kInter, bool kGin, bool kGgrid, int SHAPE>
+__device__ __forceinline__ void interior_strip(
+    const int lane, const float *__restrict__ mq /* this lane's map element(s) in the strip's first row */,
+    const float *__restrict__ gop, const float *__restrict__ bp,
+    const float2 size2 /* (W, H) as floats; (W-1, H-1) when kAlign */, const int W, const float2 gmul2 /* (gym, gxm) */,
+    float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Queue<CS> &q, const uint64_t pol_first)
+{
+    constexpr int kPitch = box_w(SHAPE), kPlane = box_w(SHAPE) * box_h(SHAPE);
+    const unsigned lt = (1u << lane) - 1u;
+    int co = -1, eo = -1;        // linear offsets of the parked south-west / south-east sums' targets; -1: nothing parked
+    float cv[CS], ev[CS];
+#pragma unroll
+    for (int k = 0; k < CS; ++k) { cv[k] = 0.f; ev[k] = 0.f; }
+
+#pragma unroll
+    for (int r = 0; r < kStripRows; ++r) {
+        float2 gxy;
+        if (kInter) gxy = *reinterpret_cast<const float2 *>(mq + r * (2 * kTW));
+        else { gxy.x = mq[r * kTW]; gxy.y = mq[kTW * kTH + r * kTW]; }
+        float go[CS];
+#pragma unroll
+        for (int k = 0; k < CS; ++k) go[k] = gop[k * (kTW * kTH) + r * kTW];
+        // unnormalise (ATen's operation order), floor, fractions
+        const float2 t = x2::add(gxy, x2::bc(1.0f));
+        const float2 ixy = kAlign ? x2::mul(x2::mul(t, x2::bc(0.5f)), size2) : x2::mul(x2::fma(t, size2, x2::bc(-1.0f)), x2::bc(0.5f));
+        const float2 fl = x2::add_rm(ixy, x2::bc(12582912.0f));              // 1.5 * 2^23: the integer part lands in the mantissa
+        const int x0 = __float_as_int(fl.x) - 0x4B400000, y0 = __float_as_int(fl.y) - 0x4B400000;
+        const float2 es = x2::sub(ixy, x2::add(fl, x2::bc(-12582912.0f)));   // (de, ds) = (ix - x0, iy - y0)
+        const float2 wn = x2::sub(x2::bc(1.0f), es);                         // (dw, dn)
+        const float de = es.x, ds = es.y, dw = wn.x, dn = wn.y;
+
+        if (kGgrid) {
+            const float *__restrict__ p0 = bp + (y0 * kPitch + x0);
+            // per tap the weights of (giy, gix) with ATen's signs: nw (-dw, -dn), ne (-de, +dn), sw (+dw, -ds), se (+de, +ds)
+            const float2 c_nw = make_float2(-dw, -dn), c_ne = make_float2(-de, dn), c_sw = make_float2(dw, -ds), c_se = es;
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < CS; ++k) {
+                const float v0 = p0[k * kPlane], v1 = p0[k * kPlane + 1], v2 = p0[k * kPlane + kPitch], v3 = p0[k * kPlane + kPitch + 1];
+                const float2 g2 = x2::bc(go[k]);
+                acc = x2::fma(x2::mul(x2::bc(v0), c_nw), g2, acc);
+                acc = x2::fma(x2::mul(x2::bc(v1), c_ne), g2, acc);
+                acc = x2::fma(x2::mul(x2::bc(v2), c_sw), g2, acc);
+                acc = x2::fma(x2::mul(x2::bc(v3), c_se), g2, acc);
+            }
+            acc = x2::mul(gmul2, acc);
+            tma::st_f32_hint(ggq, acc.y, pol_first); tma::st_f32_hint(ggq + gg_s3, acc.x, pol_first);
+            ggq += gg_s1;
+        }
+
+        if (kGin) {
+            const int o = y0 * W + x0;                      // north-west tap; the others are o + 1, o + W, o + W + 1
+            const int o_left = __shfl_up_sync(0xffffffffu, o, 1);
+            // lane l hands its east taps to lane l + 1 when that lane's north-west tap is this lane's north-east one
+            // (x0 <= W - 2 in an interior tile: "offset + 1" never wraps into the next row)
+            const bool take = lane > 0 && o_left + 1 == o;
+            const bool given = ((__ballot_sync(0xffffffffu, take) >> 1) >> lane) & 1u;
+            // (r > 0: nothing is parked in the strip's first row; the loop is unrolled, the test is free)
+            const bool chain = r > 0 && co == o;                           // the parked south-west sum lands on this row's north-west tap
+            const bool vdup = r > 0 && PWS_BWD_VDUP && co == o + W;        // ... on its south-west tap: same source row again
+            const bool broke = r > 0 && !chain && !vdup;
+            const bool e_chain = r > 0 && PWS_BWD_ECARRY && eo == o + 1, e_vdup = r > 0 && PWS_BWD_ECARRY && PWS_BWD_VDUP && eo == o + W + 1;
+            const bool e_broke = r > 0 && PWS_BWD_ECARRY && eo >= 0 && !e_chain && !e_vdup;
+            const float2 ns = make_float2(dn, ds);
+            const float2 w_w = x2::mul(x2::bc(dw), ns), w_e = x2::mul(x2::bc(de), ns);   // (nw, sw), (ne, se)
+            float et[CS], eb[CS], old_c[CS], old_e[CS];
+#pragma unroll
+            for (int k = 0; k < CS; ++k) {
+                const float2 g2 = x2::bc(go[k]);
+                float2 tb = x2::mul(w_w, g2);               // (top, bottom) of the west column
+                const float2 e2 = x2::mul(w_e, g2);         // ... of the east column
+                et[k] = e2.x; eb[k] = e2.y;
+                old_e[k] = ev[k];
+                if (e_chain) et[k] += ev[k];                // parked south-east sum: this row's north-east tap
+                if (e_vdup) eb[k] += ev[k];
+                const float2 pe = make_float2(__shfl_up_sync(0xffffffffu, et[k], 1), __shfl_up_sync(0xffffffffu, eb[k], 1));
+                if (take) tb = x2::add(tb, pe);
+                old_c[k] = cv[k];
+                if (chain) tb.x += cv[k];
+                if (vdup) tb.y += cv[k];
+                PWS_RED(at(gp[k], o), tb.x);
+                cv[k] = tb.y;
+                ev[k] = eb[k];
+            }
+            // stragglers -> queue: the north-east tap nobody took, parked sums whose chain broke
+            queue_push<CS>(q, !given, o + 1, et, lt, gp, lane);
+            if (!PWS_BWD_ECARRY) queue_push<CS>(q, !given, o + W + 1, eb, lt, gp, lane);
+            queue_push<CS>(q, broke, co, old_c, lt, gp, lane);
+            if (PWS_BWD_ECARRY) queue_push<CS>(q, e_broke, eo, old_e, lt, gp, lane);
+            co = o + W;
+            eo = (PWS_BWD_ECARRY && !given) ? o + W + 1 : -1;
+        }
+    }
+    if (kGin) {
+#pragma unroll
+        for (int k = 0; k < CS; ++k) PWS_RED(at(gp[k], co), cv[k]);   // every lane parked a south-west sum in the last row
+        if (PWS_BWD_ECARRY) queue_push<CS>(q, eo >= 0, eo, ev, lt, gp, lane);
     }
 }
 
 template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 __global__ void __launch_bounds__(kThreads, 1)
 bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View grid, const View gin, const View ggrid, const Geometry g,
-               const int tiles_x, const int tiles_y, const int total_tiles, const int n_begin, const int n_frames, const int slot, const int zero_ahead)
+               const int tiles_x, const int tiles_y, const int total_tiles, const int n_begin, const int n_frames, const int slot)
 {
     using S = Smem<CS, kGgrid>;
     constexpr int kStages = S::kStages, kMapStages = S::kMapStages;
@@ -373,14 +483,10 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     // so the replacement order favours grad_input, which is revisited between its zero-fill and its last RED.
     // (evict_last for grad_input was tried: its lines then outlive the kernel and crowd the next one out of L2.)
     const uint64_t pol_first = tma::policy_evict_first();
-    const uint64_t pol_last = tma::policy_evict_normal();
-    const uint64_t pol_box = pol_first, pol_gg = pol_first, pol_zero = pol_last;
+    const uint64_t pol_box = pol_first, pol_gg = pol_first, pol_zero = tma::policy_evict_normal();
 
     if (threadIdx.x == 0) {
         s_progress[0] = 0; s_progress[1] = 0;
-#ifdef PWS_BWD_PUBLISH
-        s_progress[2] = -1;
-#endif
         // full: the scout arrives twice -- once with the byte count of the TMA loads, once when the tile's frame is known
         // to be zero-filled by every CTA; empty: one arrival per consumer warp of the group
         for (int s = 0; s < kStages; ++s) { tma::mbar_init(full + s, 2); tma::mbar_init(empty + s, kGroupWarps); }
@@ -415,22 +521,16 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
         TileCoord tc = tile_coord(min(t, total_tiles - 1), tiles_x, tiles_xy);
         if (lane == 0 && t < total_tiles) load_map(warp, tc);  // the ring starts out empty
         int zero_seen = -1;  // bands [0, zero_seen] (index = 8 * frame + band) are known to be zero-filled by every CTA
-#ifdef PWS_EXP_CLOCKS
-        long long s_range = 0, s_wait = 0, s_issue = 0, s_zero = 0; int s_nowait = 0, s_n = 0;
-#endif
         for (int it = warp;; it += kScouts) {
             const int st = it % kStages, ph = (it / kStages) & 1;
             const int ms = it % kMapStages, mph = (it / kMapStages) & 1;
             const int ms1 = (it + kScouts) % kMapStages, mph1 = ((it + kScouts) / kMapStages) & 1;
-#ifdef PWS_EXP_CLOCKS
-            const long long q0 = clock64();
-#endif
             if (t >= total_tiles) {
                 tma::mbar_wait_relaxed(empty + st, ph ^ 1);
                 if (lane == 0) {
                     s_info[2 * st] = make_int4(0, 0, kInfoStop, 0);
                     tma::mbar_arrive(full + st); tma::mbar_arrive(full + st);
-                    progress_store(&s_progress[warp], INT_MAX - 4);  // out of tiles: let the zero-fill warp run to the end
+                    progress_store(&s_progress[warp], INT_MAX - kZeroAhead);  // out of tiles: let the zero-fill warp run to the end
                 }
                 break;
             }
@@ -455,27 +555,13 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             const int progress = 8 * tc.n + (8 * (t - tc.n * tiles_xy)) / tiles_xy;  // in eighths of a frame
             const bool want_box = kGgrid && !(info.z & (kInfoFallback | kInfoEmpty));
             const int shape = info.z & 0xff;
-#ifdef PWS_EXP_CLOCKS
-            const long long q1 = clock64();
-#endif
             tma::mbar_wait_relaxed(empty + st, ph ^ 1);
-#ifdef PWS_EXP_CLOCKS
-            const long long q2 = clock64();
-            long long q3 = q2;
-#endif
             if (lane == 0) {
                 s_info[2 * st] = info;
-#ifdef PWS_EXP_CLOCKS
-                s_info[2 * st + 1] = make_int4(tc.h0, tc.w0, (int)clock64(), 0);
-#else
                 s_info[2 * st + 1] = make_int4(tc.h0, tc.w0, 0, 0);
-#endif
                 tma::mbar_arrive_expect_tx(full + st, S::kGoutBytes + (want_box ? box_w(shape) * box_h(shape) * CS * 4 : 0));
                 tma::load_4d_hint(s_gout + (size_t)st * S::kGoutBytes, &tp.gout, full + st, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
                 if (want_box) tma::load_4d_hint(s_box + (size_t)st * S::kBoxBytes, &tp.box[shape], full + st, info.x, info.y, 0, n_begin + tc.n, pol_box);
-#ifdef PWS_EXP_CLOCKS
-                q3 = clock64();
-#endif
                 if (kGin && !(info.z & kInfoEmpty)) {
                     // the last band this tile's REDs can land in: the box rows when the taps were bounded, else the whole frame
                     const int y_hi = (info.z & kInfoFallback) ? g.H - 1 : min(info.y + box_h(shape), g.H) - 1;
@@ -483,19 +569,10 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                     // the zero-fill warp keeps `zero_ahead` bands ahead of what the scouts publish: the output position of
                     // the tile, or the band it needs if that is further on (a map that samples far away must not starve)
                     progress_store(&s_progress[warp], max(progress, need));
-#ifdef PWS_BWD_PUBLISH   // experiment (tools/exp/README.md): never run on a GPU in this form
-                    if (need > zero_seen) {
-                        // the zero-fill warp of this CTA watches the launch's counters and publishes how far every CTA
-                        // has got: the scouts never poll global memory themselves
-                        while ((zero_seen = progress_load(&s_progress[2])) < need) __nanosleep(64);
-                        __threadfence_block();
-                    }
-#else
                     if (need > zero_seen) {  // bands complete in order: every CTA fills them in order
                         while (ld_acquire(&g_zero_done[slot][need]) < gridDim.x) __nanosleep(64);
                         zero_seen = need;
                     }
-#endif
                 } else if (kGin) {
                     progress_store(&s_progress[warp], progress);
                 }
@@ -506,59 +583,17 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 tma::mbar_wait_relaxed(map_empty + ms1, mph1 ^ 1);
                 if (lane == 0) load_map(it + kScouts, tc1);
             }
-#ifdef PWS_EXP_CLOCKS
-            if (lane == 0) { s_range += q1 - q0; s_wait += q2 - q1; s_issue += q3 - q2; s_zero += clock64() - q3; s_nowait += (q2 - q1 < 200); ++s_n; }
-#endif
             t = t1; tc = tc1;
             t1 = __shfl_sync(0xffffffffu, t2, 0);
         }
-#ifdef PWS_EXP_CLOCKS
-        if (lane == 0 && (blockIdx.x % 49) == 0)
-            printf("scout cta %3d w %d: tiles %3d range %8lld wait_empty %8lld (no wait: %3d) issue %8lld zero %8lld\n", blockIdx.x, warp, s_n, s_range, s_wait, s_nowait, s_issue, s_zero);
-#endif
     } else if (warp == kZeroWarp) {
         // ===== zero-fill of grad_input, band by band, this CTA's 1/gridDim share of every band, `zero_ahead` bands ahead =====
         if (kGin) {
             const int64_t plane = (int64_t)g.H * g.W;  // dense NCHW frame (host-checked), W % 4 == 0, base 16-byte aligned
-#ifdef PWS_EXP_CLOCKS
-            long long z_trig = 0, z_st = 0, z_fence = 0;
-#endif
             const int last = n_frames * kBands - 1;
-#ifdef PWS_BWD_PUBLISH
-            // bands complete in order (every CTA fills them in order), so one acquire load per band tells how far all CTAs
-            // have got; the acquire, the block-scope fences around the shared-memory word and the scouts' mbarrier
-            // arrivals carry the ordering on to the consumers' REDs
-            int pub = -1;
-            auto advance = [&]() {
-                if (lane == 0) {
-                    const int before = pub;
-                    while (pub < last && ld_acquire(&g_zero_done[slot][pub + 1]) >= gridDim.x) ++pub;
-                    if (pub != before) { __threadfence_block(); progress_store(&s_progress[2], pub); }
-                }
-                __syncwarp();
-            };
-#endif
             for (int idx = 0; idx <= last; ++idx) {
                 const int f = idx / kBands, b = idx % kBands;
-#ifdef PWS_EXP_CLOCKS
-                const long long z0 = clock64();
-#endif
-#ifdef PWS_BWD_PUBLISH
-                // lane 0 decides, the warp follows: the condition reads volatile words, and lanes that left the loop at
-                // different iterations would meet the __syncwarp() inside advance() from different program points
-                for (;;) {
-                    int go_on = 0;
-                    if (lane == 0) go_on = max(progress_load(&s_progress[0]), progress_load(&s_progress[1])) + zero_ahead < idx;
-                    if (!__shfl_sync(0xffffffffu, go_on, 0)) break;
-                    advance();
-                    __nanosleep(256);
-                }
-#else
-                while (max(progress_load(&s_progress[0]), progress_load(&s_progress[1])) + zero_ahead < idx) __nanosleep(256);
-#endif
-#ifdef PWS_EXP_CLOCKS
-                const long long z1 = clock64();
-#endif
+                while (max(progress_load(&s_progress[0]), progress_load(&s_progress[1])) + kZeroAhead < idx) __nanosleep(256);
                 const int r0 = (b * g.H + kBands - 1) / kBands, r1 = ((b + 1) * g.H + kBands - 1) / kBands;
                 const int band_vec = (r1 - r0) * (g.W / 4);  // float4 per channel plane
                 const int share = (band_vec + gridDim.x - 1) / gridDim.x;
@@ -568,25 +603,10 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                     float4 *__restrict__ dst = reinterpret_cast<float4 *>(fp + c * plane);
                     for (int v = v0 + lane; v < v1; v += 32) tma::st_zero_v4_hint(dst + v, pol_zero);
                 }
-#ifdef PWS_EXP_CLOCKS
-                const long long z2 = clock64();
-#endif
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(&g_zero_done[slot][idx], 1u);
-#ifdef PWS_BWD_PUBLISH
-                advance();
-#endif
-#ifdef PWS_EXP_CLOCKS
-                z_trig += z1 - z0; z_st += z2 - z1; z_fence += clock64() - z2;
-#endif
             }
-#ifdef PWS_BWD_PUBLISH
-            while (__shfl_sync(0xffffffffu, pub, 0) < last) { advance(); __nanosleep(128); }
-#endif
-#ifdef PWS_EXP_CLOCKS
-            if (lane == 0 && (blockIdx.x % 49) == 0) printf("zclk cta %3d: trig %8lld store %8lld fence %8lld\n", blockIdx.x, z_trig, z_st, z_fence);
-#endif
         }
     } else {
         // ===== consumers: group `grp` owns the iterations it = grp, grp + 2, ...; a warp owns a 32 x 4 strip of the tile =====
@@ -595,136 +615,60 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
         Queue<CS> q;
         q.buf = s_queue + cw * kQueueCap;
         q.count = 0;
-        const float gxm_in = (kAlign ? Wm1 : Wf) * 0.5f, gym_in = (kAlign ? Hm1 : Hf) * 0.5f;
-#ifdef PWS_EXP_CLOCKS
-        long long c_wait = 0, c_bar = 0, c_body = 0, lat_late = 0, slack_late = 0, slack_ok = 0;
-        int n_late = 0, n_ok = 0;
-#endif
+        const float2 size2 = kAlign ? make_float2(Wm1, Hm1) : make_float2(Wf, Hf);
+        const float2 gmul2 = make_float2((kAlign ? Hm1 : Hf) * 0.5f, (kAlign ? Wm1 : Wf) * 0.5f);   // (gym, gxm)
+        // this lane's first map element, grad_output element and grad_grid element of a tile, relative to the tile
+        const int map_lane = kInter ? row0 * (2 * kTW) + 2 * (col0 + lane) : row0 * kTW + col0 + lane;
+        const int gout_lane = row0 * kTW + col0 + lane;
+        const int64_t gg_lane = kGgrid ? (int64_t)row0 * ggrid.s1 + (int64_t)(col0 + lane) * ggrid.s2 : 0;
+        const int plane_elems = g.H * g.W;   // grad_input is dense NCHW (host-checked)
         for (int it = grp;; it += kGroups) {
-            const int is = it % kStages, bs = is, ph = (it / kStages) & 1;
-#ifdef PWS_EXP_CLOCKS
-            const long long k2 = clock64();
-#endif
+            const int is = it % kStages, ph = (it / kStages) & 1;
             // one warp of the group waits on the stage's mbarrier, the others park on a hardware barrier and spin on nothing
-#ifdef PWS_BWD_NOBAR
-            tma::mbar_wait(full + is, ph);
-#else
             if (wg == 0) tma::mbar_wait(full + is, ph);
-#endif
-#ifdef PWS_EXP_CLOCKS
-            const long long k3 = clock64();
-#endif
-#ifndef PWS_BWD_NOBAR
             tma::named_bar_sync(1 + grp, kGroupWarps * 32);
-#endif
-#ifdef PWS_EXP_CLOCKS
-            const long long k4 = clock64();
-            c_wait += k3 - k2; c_bar += k4 - k3;
-            if (wg == 0 && !(s_info[2 * bs].z & kInfoStop)) {
-                const int issue = s_info[2 * bs + 1].z;
-                if (k3 - k2 > 300) { ++n_late; lat_late += (int)k3 - issue; slack_late += (int)k2 - issue; }
-                else { ++n_ok; slack_ok += (int)k2 - issue; }
-            }
-#endif
-            const int4 info = s_info[2 * bs], where = s_info[2 * bs + 1];
+            const int4 info = s_info[2 * is], where = s_info[2 * is + 1];
             if (info.z & kInfoStop) break;
-            const int n = n_begin + info.w, h0 = where.x + row0, w0 = where.y + col0;
+            const int n = n_begin + info.w;
             const int shape = info.z & 0xff;
-            const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
             const int ms = it % kMapStages;
             const float *mp = s_map + ms * kMapTileFloats;
-            const float *gop = reinterpret_cast<const float *>(s_gout + (size_t)is * S::kGoutBytes) + row0 * kTW + col0 + lane;
-            const float *bp = reinterpret_cast<const float *>(s_box + (size_t)bs * S::kBoxBytes) - (info.y * pitch + info.x);
-            const float *__restrict__ ip = (const float *)in.p + (int64_t)n * in.sN;
-            float *const gip0 = kGin ? (float *)gin.p + (int64_t)n * gin.sN : nullptr;  // this frame's grad_input (dense NCHW)
-            const int64_t gs1 = gin.s1;                                               // its channel stride
-            float *__restrict__ ggq = kGgrid ? (float *)ggrid.p + (int64_t)n * ggrid.sN + (int64_t)h0 * ggrid.s1 + (int64_t)(w0 + lane) * ggrid.s2 : nullptr;
-
-            Carry<CS> cy;
-            cy.x = 0; cy.y = 0; cy.live = false;
+            const float *gop = reinterpret_cast<const float *>(s_gout + (size_t)is * S::kGoutBytes) + gout_lane;
+            const float *box0 = reinterpret_cast<const float *>(s_box + (size_t)is * S::kBoxBytes);
+            // this frame's grad_input planes: one 64-bit base per channel, source pixels are 32-bit offsets from them
+            float *gp[CS];
+            gp[0] = kGin ? (float *)gin.p + (int64_t)n * gin.sN : nullptr;
 #pragma unroll
-            for (int k = 0; k < CS; ++k) cy.v[k] = 0.f;
+            for (int k = 1; k < CS; ++k) gp[k] = gp[k - 1] + plane_elems;
+            float *__restrict__ ggq = kGgrid ? (float *)ggrid.p + ((int64_t)n * ggrid.sN + (int64_t)where.x * ggrid.s1 + (int64_t)where.y * ggrid.s2 + gg_lane) : nullptr;
 
             if (info.z & kInfoInterior) {
-#if defined(PWS_BWD_SWP)
-                // software-pipelined rows (experiment): the grad_grid part of row r + 1 -- loads, coordinates, taps, no
-                // branches -- is written ahead of the scatter part of row r, so that the two share a basic block and
-                // the scheduler can fill the scatter's shuffle / vote latencies with it
-                float c_ix, c_iy, c_x0f, c_y0f, c_go[CS]; int c_x0, c_y0;
-                auto load_row = [&](int r, float &ix, float &iy, float &x0f, float &y0f, int &x0, int &y0, float (&go)[CS]) {
-                    float gx, gy;
-                    if (kInter) { const float2 v = *reinterpret_cast<const float2 *>(mp + (row0 + r) * (2 * kTW) + 2 * (col0 + lane)); gx = v.x; gy = v.y; }
-                    else { gx = mp[(row0 + r) * kTW + col0 + lane]; gy = mp[kTW * kTH + (row0 + r) * kTW + col0 + lane]; }
-#pragma unroll
-                    for (int k = 0; k < CS; ++k) go[k] = gop[k * (kTW * kTH) + r * kTW];
-                    ix = unnorm<kAlign>(gx, Wf, Wm1); iy = unnorm<kAlign>(gy, Hf, Hm1);
-                    floor_small(ix, x0f, x0); floor_small(iy, y0f, y0);
-                };
-                load_row(0, c_ix, c_iy, c_x0f, c_y0f, c_x0, c_y0, c_go);
-                if (kGgrid) {
-                    bwd_row<CS, false, true, false, true>(lane, true, 0xffffffffu, c_ix, c_iy, c_x0f, c_y0f, c_x0, c_y0, gxm_in, gym_in, c_go,
-                                                          bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gip0, gs1, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
-                    ggq += ggrid.s1;
+                // the box address of source pixel (x, y) is bp + y * pitch + x: fold the box origin into the base
+                switch (shape) {
+                case 0:
+                    interior_strip<CS, kAlign, kInter, kGin, kGgrid, 0>(lane, mp + map_lane, gop, box0 - (info.y * box_w(0) + info.x), size2, g.W, gmul2,
+                                                                       gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
+                    break;
+                case 1:
+                    interior_strip<CS, kAlign, kInter, kGin, kGgrid, 1>(lane, mp + map_lane, gop, box0 - (info.y * box_w(1) + info.x), size2, g.W, gmul2,
+                                                                       gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
+                    break;
+                default:
+                    interior_strip<CS, kAlign, kInter, kGin, kGgrid, 2>(lane, mp + map_lane, gop, box0 - (info.y * box_w(2) + info.x), size2, g.W, gmul2,
+                                                                       gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
+                    break;
                 }
-#pragma unroll
-                for (int r = 0; r < kStripRows; ++r) {
-                    float n_ix = 0.f, n_iy = 0.f, n_x0f = 0.f, n_y0f = 0.f, n_go[CS]; int n_x0 = 0, n_y0 = 0;
-#pragma unroll
-                    for (int k = 0; k < CS; ++k) n_go[k] = 0.f;
-                    if (r + 1 < kStripRows) {
-                        load_row(r + 1, n_ix, n_iy, n_x0f, n_y0f, n_x0, n_y0, n_go);
-                        if (kGgrid) {
-                            bwd_row<CS, false, true, false, true>(lane, true, 0xffffffffu, n_ix, n_iy, n_x0f, n_y0f, n_x0, n_y0, gxm_in, gym_in, n_go,
-                                                                  bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gip0, gs1, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
-                            ggq += ggrid.s1;
-                        }
-                    }
-                    if (kGin)
-                        bwd_row<CS, true, false, false, true>(lane, true, 0xffffffffu, c_ix, c_iy, c_x0f, c_y0f, c_x0, c_y0, gxm_in, gym_in, c_go,
-                                                              bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gip0, gs1, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
-                    c_ix = n_ix; c_iy = n_iy; c_x0f = n_x0f; c_y0f = n_y0f; c_x0 = n_x0; c_y0 = n_y0;
-#pragma unroll
-                    for (int k = 0; k < CS; ++k) c_go[k] = n_go[k];
-                }
-#else
-#pragma unroll kRowUnroll
-                for (int r = 0; r < kStripRows; ++r) {
-                    float gx, gy, go[CS];
-                    if (kInter) { const float2 v = *reinterpret_cast<const float2 *>(mp + (row0 + r) * (2 * kTW) + 2 * (col0 + lane)); gx = v.x; gy = v.y; }
-                    else { gx = mp[(row0 + r) * kTW + col0 + lane]; gy = mp[kTW * kTH + (row0 + r) * kTW + col0 + lane]; }
-#pragma unroll
-                    for (int k = 0; k < CS; ++k) go[k] = gop[k * (kTW * kTH) + r * kTW];
-                    const float ix = unnorm<kAlign>(gx, Wf, Wm1), iy = unnorm<kAlign>(gy, Hf, Hm1);
-                    float x0f, y0f; int x0, y0;
-                    floor_small(ix, x0f, x0); floor_small(iy, y0f, y0);
-                    bwd_row<CS, kGin, kGgrid, false, true>(lane, true, 0xffffffffu, ix, iy, x0f, y0f, x0, y0, gxm_in, gym_in, go,
-                                                            bp, pitch, plane, ip, in.s2, in.s1, g.H, g.W, gip0, gs1, ggq, ggrid.s3, cy, q, pol_last, pol_gg);
-                    if (kGgrid) ggq += ggrid.s1;
-                }
-#endif
             } else {
-                masked_strip<CS, kBorder, kAlign, kInter, kGin, kGgrid>(lane, info, h0, w0, row0, col0, mp, gop, bp, pitch, plane, ip, in.s2, in.s1,
-                                                                        g, gip0, gs1, ggq, ggrid.s1, ggrid.s3, cy, q, pol_last, pol_gg);
+                const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
+                const float *__restrict__ ip = (const float *)in.p + (int64_t)n * in.sN;
+                masked_strip<CS, kBorder, kAlign, kInter, kGin, kGgrid>(lane, info, where.x + row0, where.y + col0, row0, col0, mp, gop,
+                                                                        box0 - (info.y * pitch + info.x), pitch, plane, ip, in.s2, in.s1,
+                                                                        g, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
             }
-            if (kGin) {
-                if (cy.live) {
-                    const int o_cy = cy.y * g.W + cy.x;
-#pragma unroll
-                    for (int k = 0; k < CS; ++k) PWS_RED(gip0 + o_cy + k * gs1, cy.v[k]);
-                }
-                queue_flush<CS>(q, gip0, gs1, lane, pol_last);
-            }
+            if (kGin) queue_flush<CS>(q, gp, lane);
             __syncwarp();
             if (lane == 0) { tma::mbar_arrive(empty + is); tma::mbar_arrive(map_empty + ms); }
-#ifdef PWS_EXP_CLOCKS
-            c_body += clock64() - k4;
-#endif
         }
-#ifdef PWS_EXP_CLOCKS
-        if (lane == 0 && (blockIdx.x % 49) == 0 && (wg == 0 || wg == 5))
-            printf("clk cta %3d grp %d wg %d: wait %8lld bar %8lld body %8lld | late tiles %3d: latency %6lld slack %6lld | on-time tiles %3d: slack %6lld\n", blockIdx.x, grp, wg, c_wait, c_bar, c_body,
-                   n_late, n_late ? lat_late / n_late : 0, n_late ? slack_late / n_late : 0, n_ok, n_ok ? slack_ok / n_ok : 0);
-#endif
     }
     __syncthreads();
     // the last CTA to leave hands the counter slot back clean
@@ -739,30 +683,31 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     }
 }
 
-int zero_ahead()
-{
-    // how far the zero-fill runs ahead of the scatter, in eighths of a frame
-    static const int v = [] { const char *e = std::getenv("PWS_BWD_ZERO_AHEAD"); int a = e ? std::atoi(e) : 4; return a < 1 ? 1 : a; }();
-    return v;
-}
-
 template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, int total, int n0, cudaStream_t st)
 {
     auto kern = bwd_tma_kernel<CS, kBorder, kAlign, kInter, kGin, kGgrid>;
     using S = Smem<CS, kGgrid>;
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        attr_done = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};  // per instantiation, one bit per device
+    if (!ensure_dynamic_smem(reinterpret_cast<const void *>(kern), S::kTotal, attr_done)) return false;
     const int grid = total < sm_count() ? total : sm_count();
-    const int n_frames = total / (tiles_x * tiles_y);
-    const int slot = (int)(g_next_slot.fetch_add(1u, std::memory_order_relaxed) % kSyncSlots);
-    kern<<<grid, kThreads, S::kTotal, st>>>(tp, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0, n_frames, slot, zero_ahead());
+    int n_frames = total / (tiles_x * tiles_y);
+    SlotLease lease(kRingBackward, st);
+    if (!lease.ok()) return false;  // stream capture: the caller takes the memset + non-persistent kernel path
+    int slot = lease.slot();
+    // The scouts wait for EVERY CTA of the launch to have zero-filled a band of grad_input: all CTAs must be resident at
+    // the same time.  A cooperative launch makes the driver guarantee that (or refuse the launch: SM-limited contexts
+    // such as MPS partitions or green contexts, where the caller then falls back to the non-persistent kernels).
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = S::kTotal; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, tp, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0, n_frames, slot) != cudaSuccess) {
+        cudaGetLastError();
+        lease.cancel();
+        return false;
+    }
     note_launch();
     note_kernel("bwd_tma");
     return true;
@@ -831,14 +776,6 @@ bool launch_backward_tma(const BwdTmaPlan *pl, const Problem &pb, int n0, int nn
 {
     const int total = pl->tiles_x * pl->tiles_y * nn;
     if (total <= 0) return true;
-    static const bool alias = [] { const char *e = std::getenv("PWS_EXP_GIN_ALIAS"); return e && e[0] == '1'; }();
-    if (alias) {  // experiment: every frame scatters into frame 0's grad_input (L2-resident footprint; results are wrong)
-        Problem p2 = pb;
-        p2.gin.sN = 0;
-        if (pb.g.C == 3)
-            return pl->inter ? launch_ba<3, true>(pl->tp, p2, pl->tiles_x, pl->tiles_y, total, n0, st)
-                             : launch_ba<3, false>(pl->tp, p2, pl->tiles_x, pl->tiles_y, total, n0, st);
-    }
     if (pb.g.C == 3)
         return pl->inter ? launch_ba<3, true>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st)
                          : launch_ba<3, false>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st);

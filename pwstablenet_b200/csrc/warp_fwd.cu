@@ -121,33 +121,22 @@ int launch_direct(const Problem &pb, cudaStream_t st)
 }  // namespace
 
 bool launch_forward_tma(const Problem &pb, cudaStream_t st);               // warp_fwd_tma.cu (TMA-pipelined persistent)
-bool launch_forward_tile(const Problem &pb, cudaStream_t st);              // warp_fwd_tile.cu (lean / staged)
-bool launch_forward_batch(const Problem &pb, int batch, cudaStream_t st);  // warp_fwd_batch.cu
-bool launch_forward_march(const Problem &pb, cudaStream_t st);             // warp_fwd_march.cu
+bool launch_forward_tile(const Problem &pb, cudaStream_t st);              // warp_fwd_tile.cu (lean direct gather)
 
-// PWS_FWD_MODE: lean (default) | staged = warp_fwd_tile.cu; b2 | b4 = batched gather; m = marching (experiments)
-static int batch_mode()
-{
-    static const int v = [] {
-        const char *e = std::getenv("PWS_FWD_MODE");
-        if (!e || !e[0]) return 0;   // default: lean kernel (warp_fwd_tile.cu), the fastest measured
-        if (e[0] == 'b') return e[1] == '2' ? 2 : 4;
-        if (e[0] == 'm') return -1;  // marching kernel with register reuse
-        return 0;
-    }();
-    return v;
-}
-
+// Development builds (-DPWS_DEV_HOOKS, tools/build_variant.py) can force the fallback kernels through the environment;
+// the product library has no run-time switches.
 static bool force_direct()
 {
+#ifdef PWS_DEV_HOOKS
     static const bool v = [] { const char *e = std::getenv("PWS_FORCE_DIRECT"); return e && e[0] == '1'; }();
     return v;
+#else
+    return false;
+#endif
 }
 
 int launch_forward(const Problem &pb, cudaStream_t st)
 {
-    if (!force_direct() && batch_mode() < 0 && launch_forward_march(pb, st)) return PWS_OK;
-    if (!force_direct() && batch_mode() > 0 && launch_forward_batch(pb, batch_mode(), st)) return PWS_OK;
     if (!force_direct() && launch_forward_tma(pb, st)) return PWS_OK;
     if (!force_direct() && launch_forward_tile(pb, st)) { note_kernel("fwd_lean"); return PWS_OK; }
     note_kernel("fwd_direct");

@@ -1,13 +1,10 @@
-// warp_fwd_tile.cu -- staged forward warp for the reference's hot layouts.
+// warp_fwd_tile.cu -- lean direct-gather forward warp for the reference's hot layouts (fallback of warp_fwd_tma.cu).
 //
 // Call sites: R/main_new.py:106,116 (NCHW frames, planar-stored maps), :197 (NCHW
 // frames, interleaved affine_grid maps), :716 (same at native video resolution).
 // Host-checked requirements: frame and output W-contiguous and 16-byte row aligned,
 // fp32 map, C in {1,3}, f32 / f16 / bf16 frames.  Everything else takes the direct
-// kernel (warp_fwd.cu).  See pws_tile.cuh for the three phases.
-//
-// Per CTA: 64x32 output pixels, 256 threads, 8 pixels per thread; the staged frame
-// box is at most 80x40 per channel (38.4 KB for fp32 RGB).
+// kernel (warp_fwd.cu).
 #include "pws_tile.cuh"
 
 #include <cstdlib>
@@ -19,135 +16,7 @@ namespace {
 constexpr int kTW = 64, kTH = 32, kBW = 80, kBH = 40, kThreads = 256, kWarps = 8;
 constexpr int kPX = kTW / 32, kPY = kTH / kWarps;
 
-template <typename T, int CS, bool kBorder, bool kAlign>
-__global__ void __launch_bounds__(kThreads, 3)
-fwd_tile_kernel(const View in, const View grid, const View out, const Geometry g)
-{
-    constexpr int VE = 16 / (int)sizeof(T);
-    __shared__ __align__(16) T s_box[CS * kBH * kBW];
-    __shared__ __align__(16) int s_part[kWarps * 4];
-
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    const int n = blockIdx.z;
-    const int w_base = blockIdx.x * kTW + lane, h_base = blockIdx.y * kTH + wrp;
-    const float *__restrict__ gp = (const float *)grid.p + (int64_t)n * grid.sN;
-    const T *__restrict__ ip = (const T *)in.p + (int64_t)n * in.sN;
-    T *__restrict__ op = (T *)out.p + (int64_t)n * out.sN;
-    const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
-    const bool full = (blockIdx.x + 1) * kTW <= g.Wo && (blockIdx.y + 1) * kTH <= g.Ho;  // CTA-uniform
-
-    // ---- 1. map -> source indices -> tap bounding box
-    float sx[kPY][kPX], sy[kPY][kPX];
-    {
-        const bool inter = grid.s3 == 1;  // interleaved (x,y) pairs: one 8-byte load per pixel
-        const float *__restrict__ q = gp + (int64_t)h_base * grid.s1 + (int64_t)w_base * grid.s2;
-        const int64_t row = (int64_t)kWarps * grid.s1;
-        const int col = 32 * grid.s2;
-#pragma unroll
-        for (int j = 0; j < kPY; ++j)
-#pragma unroll
-            for (int i = 0; i < kPX; ++i) {
-                sx[j][i] = -4.0f; sy[j][i] = -4.0f;
-                if (full || (w_base + 32 * i < g.Wo && h_base + kWarps * j < g.Ho)) {
-                    const float *__restrict__ a = q + j * row + i * col;
-                    if (inter) {
-                        const float2 v = __ldg(reinterpret_cast<const float2 *>(a));
-                        sx[j][i] = v.x; sy[j][i] = v.y;
-                    } else {
-                        sx[j][i] = __ldg(a);
-                        sy[j][i] = __ldg(a + grid.s3);
-                    }
-                }
-            }
-    }
-    float fxlo = INFINITY, fxhi = -INFINITY, fylo = INFINITY, fyhi = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < kPY; ++j)
-#pragma unroll
-        for (int i = 0; i < kPX; ++i) {
-            sx[j][i] = src_index<kBorder, kAlign>(sx[j][i], g.W, Wf, Wm1);
-            sy[j][i] = src_index<kBorder, kAlign>(sy[j][i], g.H, Hf, Hm1);
-            if (full || (w_base + 32 * i < g.Wo && h_base + kWarps * j < g.Ho)) {
-                const float fx = floorf(sx[j][i]), fy = floorf(sy[j][i]);
-                fxlo = fminf(fxlo, fx); fxhi = fmaxf(fxhi, fx);
-                fylo = fminf(fylo, fy); fyhi = fmaxf(fyhi, fy);
-            }
-        }
-    const Box b = block_box<kWarps, VE, kBW, kBH>(fxlo, fxhi, fylo, fyhi, g.W, g.H, s_part);
-
-    // ---- 2. stage the frame box
-    if (b.fits) {
-        stage_planar<T, CS, VE, kBW, kBH, kWarps>(ip, in.s1, in.s2, b, s_box);
-        __syncthreads();
-    }
-
-    // ---- 3. gather
-    const int o_row = kWarps * out.s2, o_ch = out.s1;
-    T *__restrict__ o0 = op + (int64_t)h_base * out.s2 + w_base;
-    if (b.fits && b.all_valid && full) {
-        // interior tile: no bounds checks, no tap masks
-        const T *__restrict__ sb = s_box - (b.y0 * kBW + b.x0);
-#pragma unroll
-        for (int j = 0; j < kPY; ++j)
-#pragma unroll
-            for (int i = 0; i < kPX; ++i) {
-                const float ix = sx[j][i], iy = sy[j][i];
-                const float x0f = floorf(ix), y0f = floorf(iy);
-                const float wx1 = fsub(ix, x0f), wx0 = fsub(x0f + 1.0f, ix);
-                const float wy1 = fsub(iy, y0f), wy0 = fsub(y0f + 1.0f, iy);
-                const float nw = fmul(wx0, wy0), ne = fmul(wx1, wy0), sw = fmul(wx0, wy1), se = fmul(wx1, wy1);
-                const T *__restrict__ sp = sb + (int)y0f * kBW + (int)x0f;
-                T *__restrict__ o = o0 + (j * o_row + 32 * i);
-#pragma unroll
-                for (int c = 0; c < CS; ++c) {
-                    const T *__restrict__ pc = sp + c * (kBH * kBW);
-                    float acc = ffma(to_acc(pc[0]), nw, 0.f);  // fma with +0 keeps ATen's sign of zero
-                    acc = ffma(to_acc(pc[1]), ne, acc);
-                    acc = ffma(to_acc(pc[kBW]), sw, acc);
-                    acc = ffma(to_acc(pc[kBW + 1]), se, acc);
-                    o[c * o_ch] = from_acc<T, float>(acc);
-                }
-            }
-        return;
-    }
-#pragma unroll
-    for (int j = 0; j < kPY; ++j)
-#pragma unroll
-        for (int i = 0; i < kPX; ++i) {
-            if (!(full || (w_base + 32 * i < g.Wo && h_base + kWarps * j < g.Ho))) continue;
-            Taps<float> t;
-            make_taps(sx[j][i], sy[j][i], g.H, g.W, t);
-            T *__restrict__ o = o0 + (j * o_row + 32 * i);
-            if (b.fits) {
-                const T *__restrict__ sp = s_box + (t.y0 - b.y0) * kBW + (t.x0 - b.x0);
-#pragma unroll
-                for (int c = 0; c < CS; ++c) {
-                    const T *__restrict__ pc = sp + c * (kBH * kBW);
-                    float acc = 0.f;
-                    if (t.mask & 1u) acc = ffma(to_acc(pc[0]), t.nw, acc);
-                    if (t.mask & 2u) acc = ffma(to_acc(pc[1]), t.ne, acc);
-                    if (t.mask & 4u) acc = ffma(to_acc(pc[kBW]), t.sw, acc);
-                    if (t.mask & 8u) acc = ffma(to_acc(pc[kBW + 1]), t.se, acc);
-                    o[c * o_ch] = from_acc<T, float>(acc);
-                }
-            } else {
-                const T *__restrict__ p0 = ip + (t.y0 * in.s2 + t.x0);
-#pragma unroll
-                for (int c = 0; c < CS; ++c) {
-                    const T *__restrict__ pc = p0 + c * in.s1;
-                    float acc = 0.f;
-                    if (t.mask & 1u) acc = ffma(to_acc(ldg(pc)), t.nw, acc);
-                    if (t.mask & 2u) acc = ffma(to_acc(ldg(pc + 1)), t.ne, acc);
-                    if (t.mask & 4u) acc = ffma(to_acc(ldg(pc + in.s2)), t.sw, acc);
-                    if (t.mask & 8u) acc = ffma(to_acc(ldg(pc + in.s2 + 1)), t.se, acc);
-                    o[c * o_ch] = from_acc<T, float>(acc);
-                }
-            }
-        }
-}
-
-// Lean direct variant: same layout specialisations, taps gathered through L1 (no staging,
-// no barrier).  4 pixels per thread, 64x16 tile.  Default; PWS_FWD_MODE=staged selects the shared-memory kernel above.
+// Layout-specialised direct gather: taps through L1 (no staging, no barrier).  4 pixels per thread, 64x16 tile.
 template <typename T, int CS, bool kBorder, bool kAlign>
 #ifndef PWS_FWD_MINB
 #define PWS_FWD_MINB 5   // 48 registers, 40 warps/SM: measured ~7 % faster than 4 CTAs at 56 registers
@@ -235,34 +104,18 @@ fwd_lean_kernel(const View in, const View grid, const View out, const Geometry g
         }
 }
 
-static int fwd_mode()
-{
-    static const int v = [] {
-        const char *e = std::getenv("PWS_FWD_MODE");
-        if (e && e[0] == 's') return 0;  // staged (shared-memory box)
-        return 1;                        // lean direct: the faster of the two on B200 so far
-    }();
-    return v;
-}
-
 template <typename T, int CS>
 void launch_cs(const Problem &pb, cudaStream_t st)
 {
     const Geometry &g = pb.g;
     const bool border = g.padding == PWS_PAD_BORDER, align = g.align != 0;
-    if (fwd_mode() == 1) {
+    {
         dim3 lb((g.Wo + kTW - 1) / kTW, (g.Ho + 15) / 16, g.N);
         if (border && align) { fwd_lean_kernel<T, CS, true, true><<<lb, kThreads, 0, st>>>(pb.in, pb.grid, pb.out, g); note_launch(); }
         else if (border) { fwd_lean_kernel<T, CS, true, false><<<lb, kThreads, 0, st>>>(pb.in, pb.grid, pb.out, g); note_launch(); }
         else if (align) { fwd_lean_kernel<T, CS, false, true><<<lb, kThreads, 0, st>>>(pb.in, pb.grid, pb.out, g); note_launch(); }
         else { fwd_lean_kernel<T, CS, false, false><<<lb, kThreads, 0, st>>>(pb.in, pb.grid, pb.out, g); note_launch(); }
-        return;
     }
-    dim3 blocks((g.Wo + kTW - 1) / kTW, (g.Ho + kTH - 1) / kTH, g.N);
-    if (border && align) { fwd_tile_kernel<T, CS, true, true><<<blocks, kThreads, 0, st>>>(pb.in, pb.grid, pb.out, g); note_launch(); }
-    else if (border) { fwd_tile_kernel<T, CS, true, false><<<blocks, kThreads, 0, st>>>(pb.in, pb.grid, pb.out, g); note_launch(); }
-    else if (align) { fwd_tile_kernel<T, CS, false, true><<<blocks, kThreads, 0, st>>>(pb.in, pb.grid, pb.out, g); note_launch(); }
-    else { fwd_tile_kernel<T, CS, false, false><<<blocks, kThreads, 0, st>>>(pb.in, pb.grid, pb.out, g); note_launch(); }
 }
 
 template <typename T>
@@ -276,7 +129,7 @@ bool launch_t(const Problem &pb, cudaStream_t st)
 
 }  // namespace
 
-// Returns true when the staged kernel took the call.
+// Returns true when the lean kernel took the call.
 bool launch_forward_tile(const Problem &pb, cudaStream_t st)
 {
     const Geometry &g = pb.g;

@@ -23,6 +23,7 @@
 // T = __half / __nv_bfloat16: 16-bit frames with fp32 maps (BASELINE config 5); the box holds 16-bit elements, taps are
 // upcast, the arithmetic is fp32 and the result is rounded once.
 #include "pws_pipe.cuh"
+#include "pws_launch.cuh"
 
 #include <atomic>
 #include <cstdlib>
@@ -46,12 +47,11 @@ constexpr int kInfoStop = 1 << 11;  // info.z: no more tiles for this consumer g
 static_assert(kScouts == kGroups, "scout w feeds consumer group w (and tells it when the tiles have run out)");
 
 // Tiles are handed out dynamically, as in the backward (warp_bwd_tma.cu): the producer takes the next tile index from a
-// per-launch counter and passes it on through shared memory.  A launch owns one slot; the last CTA to leave resets it.
-constexpr int kSlots = 64;
+// per-launch counter and passes it on through shared memory.  A launch owns one slot (pws_launch.cuh: the slot is
+// leased per device and reused only after its previous launch has finished); the last CTA to leave resets it.
+constexpr int kSlots = kLaunchSlots;
 __device__ unsigned int g_tile_next[kSlots];
 __device__ unsigned int g_exit_count[kSlots];
-// one slot sequence for every instantiation of the kernel: they all share the counters above
-std::atomic<unsigned> g_next_slot{0};
 
 template <int CS, int kElem = 4> struct Smem {
     static constexpr int kBoxBytes = (kMaxBW * kMaxBH * CS * kElem + 127) / 128 * 128;
@@ -284,17 +284,12 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
 {
     auto kern = fwd_tma_kernel<T, CS, kBorder, kAlign, kInter, kCL>;
     constexpr int kSmem = Smem<CS, (int)sizeof(T)>::kTotal;
-    static bool attr_done = false;  // per instantiation
-    if (!attr_done) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        attr_done = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};  // per instantiation, one bit per device
+    if (!ensure_dynamic_smem(reinterpret_cast<const void *>(kern), kSmem, attr_done)) return false;
     const int grid = total < sm_count() ? total : sm_count();
-    const int slot = (int)(g_next_slot.fetch_add(1u, std::memory_order_relaxed) % kSlots);
-    kern<<<grid, kThreads, kSmem, st>>>(tp, pb.in, pb.out, pb.g, tiles_x, tiles_y, total, slot);
+    SlotLease lease(kRingForward, st);
+    if (!lease.ok()) return false;  // stream capture: the caller takes the non-persistent kernel
+    kern<<<grid, kThreads, kSmem, st>>>(tp, pb.in, pb.out, pb.g, tiles_x, tiles_y, total, lease.slot());
     note_launch();
     note_kernel(kCL ? "fwd_tma_cl" : sizeof(T) == 2 ? "fwd_tma_16" : "fwd_tma");
     return true;
@@ -321,8 +316,12 @@ bool launch_c(const TmaParams &tp, const Problem &pb, bool inter, int tx, int ty
 
 bool tma_disabled()
 {
+#ifdef PWS_DEV_HOOKS   // development builds only: the product library has no run-time switches
     static const bool v = [] { const char *e = std::getenv("PWS_NO_TMA"); return e && e[0] == '1'; }();
     return v;
+#else
+    return false;
+#endif
 }
 
 int sm_count()
