@@ -45,7 +45,7 @@ class HostWarpPipeline:
     def run(self, frames: torch.Tensor, maps: torch.Tensor, out: torch.Tensor, grad_out: Optional[torch.Tensor] = None,
             grad_frames: Optional[torch.Tensor] = None, grad_maps: Optional[torch.Tensor] = None) -> None:
         """All arguments are HOST tensors (pinned for real overlap).  maps / grad_maps: (N,2,Ho,Wo).
-        Returns after the last download has been enqueued and synchronised."""
+        Returns when the last download has COMPLETED: the host buffers may be read right away."""
         n = frames.size(0)
         if self.backward and (grad_out is None or grad_frames is None or grad_maps is None):
             raise ValueError("backward pipeline needs grad_out, grad_frames and grad_maps host buffers")
@@ -85,6 +85,68 @@ class HostWarpPipeline:
             k += 1
         for st in (self.s_up, self.s_run, self.s_down):
             cur.wait_stream(st)
+        # the D2H copies into the caller's buffers are asynchronous: wait for the last one before handing them back
+        self.s_down.synchronize()
+
+
+class HostInferencePipeline:
+    """The inference site (R/main_new.py:679-684,697-721) on host-resident clips: uint8 HWC frames up, the 256 x 256
+    map lattice netG emits (planar (N,2,h,w) fp32) up, ONE fused kernel per chunk (map upsample + sample + truncation to
+    uint8, `warp_fused`), uint8 HWC frames down.  12.4 MB cross the bus per 1080p frame instead of the 132.7 MB of the
+    reference's float pipeline.  Copies and kernels overlap on three streams, two device slots."""
+
+    def __init__(self, chunk: int, frame_size: Tuple[int, int], lattice_size: Tuple[int, int] = (256, 256), device=None,
+                 upsample: str = "aligned", padding_mode: str = "zeros", align_corners: bool = False):
+        self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.chunk, self.upsample, self.padding_mode, self.align = int(chunk), upsample, padding_mode, bool(align_corners)
+        H, W = frame_size
+        h, w = lattice_size
+        self.size = (H, W)
+        self.slots = []
+        for _ in range(2):
+            s = {"frames": torch.empty((chunk, H, W, 3), dtype=torch.uint8, device=self.dev),
+                 "lattice": torch.empty((chunk, 2, h, w), dtype=torch.float32, device=self.dev),
+                 "out": None}
+            s["in_ready"], s["done"], s["drained"] = (torch.cuda.Event() for _ in range(3))
+            self.slots.append(s)
+        self.s_up, self.s_run, self.s_down = (torch.cuda.Stream(self.dev) for _ in range(3))
+
+    def run(self, frames: torch.Tensor, lattices: torch.Tensor, out: torch.Tensor) -> None:
+        """frames, out: (N,H,W,3) uint8 host tensors (cv2 layout); lattices: (N,2,h,w) fp32 host tensor (netG's stage-3
+        map).  Returns when `out` is complete."""
+        from .compose import warp_fused
+        n = frames.size(0)
+        cur = torch.cuda.current_stream(self.dev)
+        for st in (self.s_up, self.s_run, self.s_down):
+            st.wait_stream(cur)
+        k = 0
+        for b in range(0, n, self.chunk):
+            e = min(n, b + self.chunk)
+            m = e - b
+            s = self.slots[k & 1]
+            with torch.cuda.stream(self.s_up):
+                if k >= 2:
+                    self.s_up.wait_event(s["done"])
+                s["frames"][:m].copy_(frames[b:e], non_blocking=True)
+                s["lattice"][:m].copy_(lattices[b:e], non_blocking=True)
+                s["in_ready"].record(self.s_up)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(s["in_ready"])
+                if k >= 2:
+                    self.s_run.wait_event(s["drained"])
+                res = warp_fused(s["frames"][:m].permute(0, 3, 1, 2), drift=s["lattice"][:m].permute(0, 2, 3, 1),
+                                 upsample=self.upsample, out_size=self.size, padding_mode=self.padding_mode,
+                                 align_corners=self.align, out_dtype=torch.uint8, out_channels_last=True)
+                s["out"] = res.permute(0, 2, 3, 1)    # (m,H,W,3) dense; kept alive until the download has run
+                s["done"].record(self.s_run)
+            with torch.cuda.stream(self.s_down):
+                self.s_down.wait_event(s["done"])
+                out[b:e].copy_(s["out"], non_blocking=True)
+                s["drained"].record(self.s_down)
+            k += 1
+        for st in (self.s_up, self.s_run, self.s_down):
+            cur.wait_stream(st)
+        self.s_down.synchronize()
 
 
 def warp_host(frames: torch.Tensor, maps: torch.Tensor, grad_out: Optional[torch.Tensor] = None, chunk: int = 2,
@@ -99,5 +161,4 @@ def warp_host(frames: torch.Tensor, maps: torch.Tensor, grad_out: Optional[torch
     gf = torch.empty_like(frames).pin_memory() if grad_out is not None else None
     gm = torch.empty_like(maps).pin_memory() if grad_out is not None else None
     pipe.run(frames, maps, out, grad_out, gf, gm)
-    torch.cuda.synchronize(pipe.dev)
     return out, gf, gm
