@@ -238,7 +238,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--min-seconds", type=float, default=1.0, help="lower bound of the device-timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="headline", choices=["headline", "train", "clip"],
+                    help="headline: the BASELINE metric (default); train: BASELINE config 3 (netG training step, DDP); "
+                         "clip: BASELINE config 4 (300-frame 1080p clip inference, frame-sharded)")
     args = ap.parse_args()
+    if args.config != "headline":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        if args.config == "train":
+            from harness import train_step
+            return train_step.run(args)
+        from harness import clip_inference
+        return clip_inference.run(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -147,6 +147,26 @@ int pws_warp2d_forward_fused(const pws_tensor *in, const pws_map_spec *spec, pws
 /* Debug / parity: writes the map the fused kernel uses into map_out (N,Ho,Wo,2) f32. */
 int pws_compose_map(const pws_map_spec *spec, int64_t n, pws_tensor *map_out, void *stream);
 
+/* ---- K maps, one frame, one launch (north_star "map composition across cascade
+ * stages fused into the sample") ---------------------------------------------------------------------------------
+ * Replaces the reference's per-stage sequence R/main_new.py:103-110 (and :112-119)
+ *     for nl in range(num_layer): fake[nl] = grid_sample((frame + 1) * 127.5, grid[nl]) / 127.5 - 1
+ * and its autograd (R/main_new.py:214): every stage's map samples the SAME frame, which is read once; the scaled frame
+ * and the unscaled samples never reach HBM.
+ *     outs[k]   = sample((in + pre_add) * pre_mul, grids[k]) * (1 / post_div) + post_add        k < n_stages <= 4
+ *     ggrids[k] = d outs[k] / d grids[k] applied to gouts[k]      (entries may be NULL)
+ *     gin       = sum_k d outs[k] / d in applied to gouts[k]      (may be NULL; dense NCHW, zero-filled by the library)
+ * f32 frames and maps, C in {1, 3}, any strides.  `1 / post_div` is the rounded fp32 reciprocal torch's
+ * `tensor / scalar` multiplies by, so the results equal the reference's sequence of torch calls bit for bit.
+ * (0, 1, 1, 0) switches the scales off. */
+int pws_warp2d_stages_forward(const pws_tensor *in, const pws_tensor *const *grids, pws_tensor *const *outs, int n_stages,
+                              float pre_add, float pre_mul, float post_div, float post_add,
+                              int padding, int align_corners, void *stream);
+int pws_warp2d_stages_backward(const pws_tensor *const *gouts, const pws_tensor *in, const pws_tensor *const *grids,
+                               pws_tensor *gin, pws_tensor *const *ggrids, int n_stages,
+                               float pre_add, float pre_mul, float post_div, float post_add,
+                               int padding, int align_corners, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpwswarp.so")
-SOURCES = ["capi.cu", "pws_launch.cu", "warp_fwd.cu", "warp_fwd_tile.cu", "warp_fwd_tma.cu", "warp_bwd.cu", "warp_bwd_lean.cu", "warp_bwd_tma.cu", "warp_fused.cu"]
+SOURCES = ["capi.cu", "pws_launch.cu", "warp_fwd.cu", "warp_fwd_tile.cu", "warp_fwd_tma.cu", "warp_bwd.cu", "warp_bwd_lean.cu", "warp_bwd_tma.cu", "warp_fused.cu", "warp_stages.cu"]
 HEADERS = ["pws_common.cuh", "pws_tile.cuh", "pws_tma.cuh", "pws_pipe.cuh", "pws_launch.cuh", "pws_f32x2.cuh", os.path.join("..", "..", "include", "pwswarp.h")]
 
 NVCC_FLAGS = [

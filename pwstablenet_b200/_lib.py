@@ -22,6 +22,8 @@ EXPORTS = (
     "pws_warp2d_taps",
     "pws_warp2d_forward_fused",
     "pws_compose_map",
+    "pws_warp2d_stages_forward",
+    "pws_warp2d_stages_backward",
 )
 
 
@@ -86,6 +88,13 @@ def load() -> ctypes.CDLL:
     lib.pws_warp2d_forward_fused.argtypes = [P, S, P, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.pws_compose_map.restype = ctypes.c_int
     lib.pws_compose_map.argtypes = [S, ctypes.c_int64, P, ctypes.c_void_p]
+    PP = ctypes.POINTER(P)
+    lib.pws_warp2d_stages_forward.restype = ctypes.c_int
+    lib.pws_warp2d_stages_forward.argtypes = [P, PP, PP, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.pws_warp2d_stages_backward.restype = ctypes.c_int
+    lib.pws_warp2d_stages_backward.argtypes = [PP, P, PP, P, PP, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                               ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     got = lib.pws_abi_version()
     if got != ABI_VERSION:
         raise RuntimeError(f"pwstablenet_b200: libpwswarp.so has ABI {got}, expected {ABI_VERSION}; rebuild it")

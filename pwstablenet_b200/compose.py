@@ -126,3 +126,74 @@ def warp_fused(frame: torch.Tensor, drift: Optional[torch.Tensor] = None, base: 
                                           _PADDING[padding_mode], int(bool(align_corners)), _stream(frame))
     _lib.check(rc)
     return out
+
+
+# ---- K maps, one frame, one launch: forward + backward (include/pwswarp.h, csrc/warp_stages.cu) ---------------------
+def _desc_ptrs(tensors, keep):
+    arr = (ctypes.POINTER(_lib.PwsTensor) * len(tensors))()
+    for i, t in enumerate(tensors):
+        if t is None:
+            arr[i] = None
+        else:
+            d = _desc(t)
+            keep.append(d)
+            arr[i] = ctypes.pointer(d)
+    return arr
+
+
+class _WarpStages(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, frame, padding, align_corners, pre_add, pre_mul, post_div, post_add, *grids):
+        lib = _lib.load()
+        k = len(grids)
+        n, c = frame.size(0), frame.size(1)
+        outs = [torch.empty((n, c, g.size(1), g.size(2)), dtype=frame.dtype, device=frame.device) for g in grids]
+        keep = []
+        with torch.cuda.device_of(frame):
+            rc = lib.pws_warp2d_stages_forward(ctypes.byref(_desc(frame)), _desc_ptrs(grids, keep), _desc_ptrs(outs, keep), k,
+                                               pre_add, pre_mul, post_div, post_add, padding, int(align_corners), _stream(frame))
+        _lib.check(rc)
+        ctx.save_for_backward(frame, *grids)
+        ctx.args = (padding, align_corners, pre_add, pre_mul, post_div, post_add)
+        return tuple(outs)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gouts):
+        lib = _lib.load()
+        frame, *grids = ctx.saved_tensors
+        padding, align_corners, pre_add, pre_mul, post_div, post_add = ctx.args
+        k = len(grids)
+        gouts = [g if g is not None else torch.zeros((frame.size(0), frame.size(1), grids[i].size(1), grids[i].size(2)),
+                                                     dtype=frame.dtype, device=frame.device) for i, g in enumerate(gouts)]
+        from .functional import _like_layout
+        gin = torch.empty(frame.size(), dtype=frame.dtype, device=frame.device) if ctx.needs_input_grad[0] else None
+        ggrids = [_like_layout(grids[i]) if ctx.needs_input_grad[7 + i] else None for i in range(k)]
+        keep = []
+        with torch.cuda.device_of(frame):
+            rc = lib.pws_warp2d_stages_backward(_desc_ptrs(gouts, keep), ctypes.byref(_desc(frame)), _desc_ptrs(grids, keep),
+                                                ctypes.byref(_desc(gin)) if gin is not None else None, _desc_ptrs(ggrids, keep), k,
+                                                pre_add, pre_mul, post_div, post_add, padding, int(align_corners), _stream(frame))
+        _lib.check(rc)
+        return (gin, None, None, None, None, None, None, *ggrids)
+
+
+def warp_stages(frame: torch.Tensor, grids, padding_mode: str = "zeros", align_corners: bool = False,
+                pre: Tuple[float, float] = (0.0, 1.0), post: Tuple[float, float] = (1.0, 0.0)):
+    """[grid_sample((frame + pre[0]) * pre[1], g, 'bilinear', padding_mode, align_corners) / post[0] + post[1] for g in grids]
+    in ONE kernel launch that reads the frame once, with autograd to every map (and to the frame when it asks for it).
+
+    The reference's per-stage loop R/main_new.py:103-110: `warp_stages(rgb, grid1, pre=(1, 127.5), post=(127.5, -1))`.
+    Up to 4 maps; f32, C in {1, 3}.  Values and gradients are bit-identical to the sequence of torch calls it replaces."""
+    grids = list(grids)
+    if not 1 <= len(grids) <= 4:
+        raise ValueError("warp_stages: 1 to 4 maps")
+    if padding_mode not in ("zeros", "border"):
+        raise NotImplementedError("warp_stages: padding_mode must be 'zeros' or 'border'")
+    if not frame.is_cuda or frame.dtype != torch.float32 or frame.dim() != 4:
+        raise RuntimeError("warp_stages: frame must be a 4-D float32 CUDA tensor (no CPU fallback)")
+    for g in grids:
+        if not g.is_cuda or g.dtype != torch.float32 or g.dim() != 4 or g.size(3) != 2 or g.size(0) != frame.size(0):
+            raise RuntimeError("warp_stages: every map must be a float32 CUDA tensor of sizes (N, Ho, Wo, 2)")
+    return _WarpStages.apply(frame, _PADDING[padding_mode], bool(align_corners), float(pre[0]), float(pre[1]),
+                             float(post[0]), float(post[1]), *grids)

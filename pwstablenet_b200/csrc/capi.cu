@@ -159,6 +159,17 @@ int finish(const char *what)
 }  // namespace pws
 
 namespace pws {
+static int make_scale(float pre_add, float pre_mul, float post_div, float post_add, StageScale *sc)
+{
+    if (post_div == 0.0f) { set_error("stages: post_div must not be 0"); return PWS_EINVAL; }
+    sc->pre_add = pre_add; sc->pre_mul = pre_mul;
+    sc->post_mul = 1.0f / post_div;   // fp32 division: the reciprocal torch's `tensor / scalar` kernel multiplies by
+    sc->post_add = post_add;
+    sc->has_pre = !(pre_add == 0.0f && pre_mul == 1.0f);
+    sc->has_post = !(post_div == 1.0f && post_add == 0.0f);
+    return PWS_OK;
+}
+
 int launch_forward_fused(const View &in, int in_dtype, const MapSpec &m, const View &out, int out_dtype,
                          const Geometry &g, cudaStream_t st);
 int launch_compose_map(const MapSpec &m, const View &out, int N, int Ho, int Wo, cudaStream_t st);
@@ -339,6 +350,90 @@ int pws_compose_map(const pws_map_spec *spec, int64_t n, pws_tensor *map_out, vo
     if (!dg.ok) { set_error("compose_map: cannot select cuda:%d", map_out->device); return PWS_ECUDA; }
     PWS_TRY(launch_compose_map(m, vout, (int)n, (int)map_out->size[1], (int)map_out->size[2], (cudaStream_t)stream));
     return finish("compose_map");
+}
+
+__attribute__((visibility("default")))
+int pws_warp2d_stages_forward(const pws_tensor *in, const pws_tensor *const *grids, pws_tensor *const *outs, int n_stages,
+                              float pre_add, float pre_mul, float post_div, float post_add,
+                              int padding, int align_corners, void *stream)
+{
+    PWS_TRY(check_modes(PWS_INTERP_BILINEAR, padding));
+    if (!in || !grids || !outs) { set_error("stages forward: null argument"); return PWS_EINVAL; }
+    if (n_stages < 1 || n_stages > kMaxStages) { set_error("stages forward: n_stages must be 1..%d", kMaxStages); return PWS_EINVAL; }
+    if (in->dtype != PWS_F32) { set_error("stages forward: f32 frames only"); return PWS_EUNSUPPORTED; }
+    View vin;
+    PWS_TRY(make_view(in, "input", &vin));
+    StageViews sv{};
+    Geometry g{};
+    for (int k = 0; k < n_stages; ++k) {
+        PWS_TRY(check_pair(in, grids[k]));
+        if (!outs[k]) { set_error("stages forward: null output %d", k); return PWS_EINVAL; }
+        if (grids[k]->dtype != PWS_F32 || outs[k]->dtype != PWS_F32) { set_error("stages forward: f32 maps and outputs only"); return PWS_EUNSUPPORTED; }
+        if (k && (grids[k]->size[1] != grids[0]->size[1] || grids[k]->size[2] != grids[0]->size[2])) { set_error("stages forward: all maps must have the same size"); return PWS_EINVAL; }
+        PWS_TRY(make_view(grids[k], "grid", &sv.map[k]));
+        PWS_TRY(make_view(outs[k], "output", &sv.io[k]));
+        PWS_TRY(same_shape(outs[k], in->size[0], in->size[1], grids[k]->size[1], grids[k]->size[2], "output"));
+        if (outs[k]->device != in->device) { set_error("stages forward: output must be on the input's device"); return PWS_EINVAL; }
+    }
+    fill_geometry(in, grids[0], padding, align_corners, &g);
+    StageScale sc;
+    PWS_TRY(make_scale(pre_add, pre_mul, post_div, post_add, &sc));
+    if ((int64_t)g.N * g.C * g.Ho * g.Wo == 0) return PWS_OK;
+    DeviceGuard dg(in->device);
+    if (!dg.ok) { set_error("stages forward: cannot select cuda:%d", in->device); return PWS_ECUDA; }
+    PWS_TRY(launch_stages_forward(vin, sv, n_stages, g, sc, (cudaStream_t)stream));
+    return finish("stages forward");
+}
+
+__attribute__((visibility("default")))
+int pws_warp2d_stages_backward(const pws_tensor *const *gouts, const pws_tensor *in, const pws_tensor *const *grids,
+                               pws_tensor *gin, pws_tensor *const *ggrids, int n_stages,
+                               float pre_add, float pre_mul, float post_div, float post_add,
+                               int padding, int align_corners, void *stream)
+{
+    PWS_TRY(check_modes(PWS_INTERP_BILINEAR, padding));
+    if (!in || !grids || !gouts || !ggrids) { set_error("stages backward: null argument"); return PWS_EINVAL; }
+    if (n_stages < 1 || n_stages > kMaxStages) { set_error("stages backward: n_stages must be 1..%d", kMaxStages); return PWS_EINVAL; }
+    if (in->dtype != PWS_F32) { set_error("stages backward: f32 frames only"); return PWS_EUNSUPPORTED; }
+    View vin, vgin{};
+    PWS_TRY(make_view(in, "input", &vin));
+    StageViews sv{};
+    Geometry g{};
+    for (int k = 0; k < n_stages; ++k) {
+        PWS_TRY(check_pair(in, grids[k]));
+        if (!gouts[k]) { set_error("stages backward: null grad_output %d", k); return PWS_EINVAL; }
+        if (grids[k]->dtype != PWS_F32 || gouts[k]->dtype != PWS_F32) { set_error("stages backward: f32 only"); return PWS_EUNSUPPORTED; }
+        if (k && (grids[k]->size[1] != grids[0]->size[1] || grids[k]->size[2] != grids[0]->size[2])) { set_error("stages backward: all maps must have the same size"); return PWS_EINVAL; }
+        PWS_TRY(make_view(grids[k], "grid", &sv.map[k]));
+        PWS_TRY(make_view(gouts[k], "grad_output", &sv.io[k]));
+        PWS_TRY(same_shape(gouts[k], in->size[0], in->size[1], grids[k]->size[1], grids[k]->size[2], "grad_output"));
+        if (ggrids[k]) {
+            if (ggrids[k]->dtype != PWS_F32) { set_error("stages backward: f32 grad_grid only"); return PWS_EUNSUPPORTED; }
+            PWS_TRY(make_view(ggrids[k], "grad_grid", &sv.gg[k]));
+            PWS_TRY(same_shape(ggrids[k], grids[k]->size[0], grids[k]->size[1], grids[k]->size[2], 2, "grad_grid"));
+        }
+    }
+    if (gin) {
+        PWS_TRY(make_view(gin, "grad_input", &vgin));
+        PWS_TRY(same_shape(gin, in->size[0], in->size[1], in->size[2], in->size[3], "grad_input"));
+        const int64_t C = in->size[1], H = in->size[2], W = in->size[3];
+        const bool dense = gin->dtype == PWS_F32 && gin->stride[3] == 1 && gin->stride[2] == W && gin->stride[1] == H * W &&
+                           (gin->stride[0] == C * H * W || in->size[0] <= 1);
+        if (!dense) { set_error("grad_input: must be f32 (N,C,H,W)-contiguous (the library zero-fills it)"); return PWS_EINVAL; }
+        vgin.sN = C * H * W;
+    }
+    fill_geometry(in, grids[0], padding, align_corners, &g);
+    StageScale sc;
+    PWS_TRY(make_scale(pre_add, pre_mul, post_div, post_add, &sc));
+    DeviceGuard dg(in->device);
+    if (!dg.ok) { set_error("stages backward: cannot select cuda:%d", in->device); return PWS_ECUDA; }
+    if (g.N == 0) return PWS_OK;
+    if ((int64_t)g.C * g.Ho * g.Wo == 0) {
+        if (gin && (int64_t)g.C * g.H * g.W > 0) cudaMemsetAsync(gin->data, 0, (size_t)(in->size[0] * vgin.sN * 4), (cudaStream_t)stream);
+        return PWS_OK;
+    }
+    PWS_TRY(launch_stages_backward(vin, sv, n_stages, vgin, gin != nullptr, g, sc, (cudaStream_t)stream));
+    return finish("stages backward");
 }
 
 }  // extern "C"

@@ -152,6 +152,21 @@ struct MapSpec {  // kernel-side form of pws_map_spec (warp_fused.cu)
     int has_pre, has_post;
 };
 
+// K maps applied to one frame (warp_stages.cu)
+constexpr int kMaxStages = 4;
+struct StageViews {
+    View map[kMaxStages];
+    View io[kMaxStages];     // forward: outputs; backward: grad_outputs
+    View gg[kMaxStages];     // backward: grad_grids (p == nullptr: not wanted)
+};
+struct StageScale {
+    float pre_add, pre_mul, post_mul, post_add;
+    int has_pre, has_post;
+};
+int launch_stages_forward(const View &in, const StageViews &sv, int K, const Geometry &g, const StageScale &sc, cudaStream_t st);
+int launch_stages_backward(const View &in, const StageViews &sv, int K, const View &gin, bool want_gin, const Geometry &g,
+                           const StageScale &sc, cudaStream_t st);
+
 int launch_forward(const Problem &pb, cudaStream_t st);
 int launch_backward(const Problem &pb, cudaStream_t st);
 int launch_taps(const View &grid, const Geometry &g, int32_t *x0, int32_t *y0, uint8_t *mask, float *w, cudaStream_t st);
