@@ -71,7 +71,9 @@ def load() -> ctypes.CDLL:
             "`python -m pwstablenet_b200._build` (needs nvcc 12.9); there is no CPU or PyTorch fallback."
         )
     lib = ctypes.CDLL(LIB_PATH)
-    P = ctypes.POINTER(PwsTensor)
+    # pws_tensor pointers are declared void*: callers pass either byref(PwsTensor) or the hand-packed ten-word array of
+    # functional._desc (same bytes, much cheaper to build)
+    P = ctypes.c_void_p
     lib.pws_abi_version.restype = ctypes.c_int
     lib.pws_last_error.restype = ctypes.c_char_p
     lib.pws_launch_count.restype = ctypes.c_uint64
@@ -88,7 +90,7 @@ def load() -> ctypes.CDLL:
     lib.pws_warp2d_forward_fused.argtypes = [P, S, P, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.pws_compose_map.restype = ctypes.c_int
     lib.pws_compose_map.argtypes = [S, ctypes.c_int64, P, ctypes.c_void_p]
-    PP = ctypes.POINTER(P)
+    PP = ctypes.c_void_p
     lib.pws_warp2d_stages_forward.restype = ctypes.c_int
     lib.pws_warp2d_stages_forward.argtypes = [P, PP, PP, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                               ctypes.c_int, ctypes.c_int, ctypes.c_void_p]

@@ -261,7 +261,13 @@ int pws_warp2d_backward(const pws_tensor *gout, const pws_tensor *in, const pws_
     if (gin) {
         PWS_TRY(make_view(gin, "grad_input", &pb.gin));
         PWS_TRY(same_shape(gin, in->size[0], in->size[1], in->size[2], in->size[3], "grad_input"));
-        if (gin->dtype != in->dtype || gin->device != in->device) { set_error("grad_input: dtype/device must equal the input's"); return PWS_EINVAL; }
+        // 16-bit frames: grad_input is an fp32 accumulation buffer that the caller rounds once (see launch_16bit)
+        const bool half_in = in->dtype == PWS_F16 || in->dtype == PWS_BF16;
+        if ((half_in ? gin->dtype != PWS_F32 : gin->dtype != in->dtype) || gin->device != in->device) {
+            set_error(half_in ? "grad_input: 16-bit frames accumulate into an f32 (N,C,H,W) buffer on the input's device"
+                              : "grad_input: dtype/device must equal the input's");
+            return PWS_EINVAL;
+        }
         const int64_t C = in->size[1], H = in->size[2], W = in->size[3];
         const bool dense = gin->stride[3] == 1 && gin->stride[2] == W && gin->stride[1] == H * W &&
                            (gin->stride[0] == C * H * W || in->size[0] <= 1);
@@ -281,7 +287,7 @@ int pws_warp2d_backward(const pws_tensor *gout, const pws_tensor *in, const pws_
     if ((int64_t)pb.g.C * pb.g.Ho * pb.g.Wo == 0) {
         // nothing scatters; grad_input is still defined (all zeros)
         if (gin && (int64_t)pb.g.C * pb.g.H * pb.g.W > 0) {
-            cudaError_t e = cudaMemsetAsync(gin->data, 0, (size_t)(in->size[0] * pb.gin.sN * elem_size(in->dtype)), (cudaStream_t)stream);
+            cudaError_t e = cudaMemsetAsync(gin->data, 0, (size_t)(in->size[0] * pb.gin.sN * elem_size(gin->dtype)), (cudaStream_t)stream);
             if (e != cudaSuccess) { set_error("backward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return PWS_ECUDA; }
         }
         return PWS_OK;

@@ -259,13 +259,33 @@ int launch_typed(const Problem &pb, cudaStream_t st)
     return PWS_OK;
 }
 
+// 16-bit frames and grad_output with an fp32 map (BASELINE config 5): fp32 arithmetic, fp32 grad_grid and an fp32
+// grad_input ACCUMULATION buffer (capi.cu requires it), which the caller rounds to the frame type once -- summing a
+// pixel's contributions in bf16 would round after every atomic.
+int launch_16bit(const Problem &pb, cudaStream_t st)
+{
+    if (!backward_lean_eligible(pb)) {
+        set_error("backward: 16-bit frames need W-contiguous frames / grad_output, C in {1,3} and an fp32 map");
+        return PWS_EUNSUPPORTED;
+    }
+    const Geometry &g = pb.g;
+    if (pb.want_gin) {
+        cudaError_t e = cudaMemsetAsync(pb.gin.p, 0, (size_t)g.N * pb.gin.sN * sizeof(float), st);
+        if (e != cudaSuccess) { set_error("backward: cudaMemsetAsync: %s", cudaGetErrorString(e)); return PWS_ECUDA; }
+    }
+    note_kernel("bwd_lean_16");
+    launch_backward_lean(pb, 0, g.N, st);
+    return PWS_OK;
+}
+
 }  // namespace
 
 int launch_backward(const Problem &pb, cudaStream_t st)
 {
     if (!pb.want_gin && !pb.want_ggrid) return PWS_OK;
+    if ((pb.in_dtype == PWS_F16 || pb.in_dtype == PWS_BF16) && pb.grid_dtype == PWS_F32) return launch_16bit(pb, st);
     if (pb.in_dtype != pb.grid_dtype) {
-        set_error("backward: frame and map dtypes must match (got %d, %d)", pb.in_dtype, pb.grid_dtype);
+        set_error("backward: frame and map dtypes must match, or 16-bit frames with an fp32 map (got %d, %d)", pb.in_dtype, pb.grid_dtype);
         return PWS_EUNSUPPORTED;
     }
     if (pb.in_dtype == PWS_F32) return launch_typed<float>(pb, st);

@@ -25,11 +25,11 @@ struct Carry {
 };
 
 // One output row of a warp.  kMasked=false: every lane is a real pixel with 4 valid taps.
-template <int CS, bool kGin, bool kGgrid, bool kMasked>
+template <typename T, int CS, bool kGin, bool kGgrid, bool kMasked>
 __device__ __forceinline__ void row_body(
     const int lane, const bool px_ok, const unsigned live,
     const float ix, const float iy, const float gxm, const float gym, const float (&go)[CS],
-    const float *__restrict__ ip, const int sH, const int i_ch, const int H, const int W,
+    const T *__restrict__ ip, const int sH, const int i_ch, const int H, const int W,
     float *__restrict__ gip, const int gi_ch,
     float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy, int2 *__restrict__ queue)
 {
@@ -49,12 +49,12 @@ __device__ __forceinline__ void row_body(
         float gix = 0.f, giy = 0.f;
 #pragma unroll
         for (int k = 0; k < CS; ++k) {
-            const float *__restrict__ pc = ip + (k * i_ch + o_nw);
+            const T *__restrict__ pc = ip + (k * i_ch + o_nw);
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-            if (!kMasked || (mask & 1u)) v0 = __ldg(pc);
-            if (!kMasked || (mask & 2u)) v1 = __ldg(pc + 1);
-            if (!kMasked || (mask & 4u)) v2 = __ldg(pc + sH);
-            if (!kMasked || (mask & 8u)) v3 = __ldg(pc + sH + 1);
+            if (!kMasked || (mask & 1u)) v0 = to_acc(ldg(pc));
+            if (!kMasked || (mask & 2u)) v1 = to_acc(ldg(pc + 1));
+            if (!kMasked || (mask & 4u)) v2 = to_acc(ldg(pc + sH));
+            if (!kMasked || (mask & 8u)) v3 = to_acc(ldg(pc + sH + 1));
             // ATen's statement order: t = v*d rounded, then one fma with gOut
             if (!kMasked || (mask & 1u)) { gix = ffma(-fmul(v0, dn), go[k], gix); giy = ffma(-fmul(v0, dw), go[k], giy); }
             if (!kMasked || (mask & 2u)) { gix = ffma(fmul(v1, dn), go[k], gix);  giy = ffma(-fmul(v1, de), go[k], giy); }
@@ -116,7 +116,9 @@ __device__ __forceinline__ void row_body(
     }
 }
 
-template <int CS, bool kBorder, bool kAlign, bool kGin, bool kGgrid>
+// T: element type of the frame and of grad_output (float, or __half / __nv_bfloat16 with fp32 maps -- BASELINE config 5);
+// the arithmetic, grad_grid and the grad_input accumulation buffer are fp32 whatever T is.
+template <typename T, int CS, bool kBorder, bool kAlign, bool kGin, bool kGgrid>
 #ifndef PWS_BWD_MINB
 #define PWS_BWD_MINB 4   // 64 registers, 32 warps/SM: measured 5-9 % faster than 3 CTAs at 80 registers
 #endif
@@ -136,14 +138,14 @@ bwd_lean_kernel(const View gout, const View in, const View grid, const View gin,
     const int rows = min(kRows, g.Ho - h0);
     const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
 
-    const float *__restrict__ ip = (const float *)in.p + (int64_t)n * in.sN;
+    const T *__restrict__ ip = (const T *)in.p + (int64_t)n * in.sN;
     float *__restrict__ gip = kGin ? (float *)gin.p + (int64_t)n * gin.sN : nullptr;
     const int sH = in.s2;
     const int i_ch = in.s1, gi_ch = kGin ? gin.s1 : 0, go_ch = gout.s1;  // 32-bit in-frame offsets (validated on the host)
 
     const bool inter = grid.s3 == 1;
     const float *__restrict__ gq = (const float *)grid.p + (int64_t)n * grid.sN + (int64_t)h0 * grid.s1 + (int64_t)w * grid.s2;
-    const float *__restrict__ goq = (const float *)gout.p + (int64_t)n * gout.sN + (int64_t)h0 * gout.s2 + w;
+    const T *__restrict__ goq = (const T *)gout.p + (int64_t)n * gout.sN + (int64_t)h0 * gout.s2 + w;
     float *__restrict__ ggq = kGgrid ? (float *)ggrid.p + (int64_t)n * ggrid.sN + (int64_t)h0 * ggrid.s1 + (int64_t)w * ggrid.s2 : nullptr;
 
     Carry<CS> cy;
@@ -159,7 +161,7 @@ bwd_lean_kernel(const View gout, const View in, const View grid, const View gin,
         if (inter) { const float2 v = __ldg(reinterpret_cast<const float2 *>(gq)); gx_n = v.x; gy_n = v.y; }
         else { gx_n = __ldg(gq); gy_n = __ldg(gq + grid.s3); }
 #pragma unroll
-        for (int k = 0; k < CS; ++k) go_n[k] = __ldg(goq + k * go_ch);
+        for (int k = 0; k < CS; ++k) go_n[k] = to_acc(ldg(goq + k * go_ch));
     }
 
     for (int r = 0; r < rows; ++r) {
@@ -172,16 +174,16 @@ bwd_lean_kernel(const View gout, const View in, const View grid, const View gin,
             if (inter) { const float2 v = __ldg(reinterpret_cast<const float2 *>(gq)); gx_n = v.x; gy_n = v.y; }
             else { gx_n = __ldg(gq); gy_n = __ldg(gq + grid.s3); }
 #pragma unroll
-            for (int k = 0; k < CS; ++k) go_n[k] = __ldg(goq + k * go_ch);
+            for (int k = 0; k < CS; ++k) go_n[k] = to_acc(ldg(goq + k * go_ch));
         }
         float gxm, gym;
         const float ix = src_index_grad<kBorder, kAlign>(gx, Wf, Wm1, &gxm);
         const float iy = src_index_grad<kBorder, kAlign>(gy, Hf, Hm1, &gym);
         const bool inside = col_ok && ix >= 0.0f && ix < Wm1 && iy >= 0.0f && iy < Hm1;  // floor in [0, size-2]
         if (__all_sync(0xffffffffu, inside))
-            row_body<CS, kGin, kGgrid, false>(lane, true, live, ix, iy, gxm, gym, go, ip, sH, i_ch, g.H, g.W, gip, gi_ch, ggq, ggrid.s3, cy, queue);
+            row_body<T, CS, kGin, kGgrid, false>(lane, true, live, ix, iy, gxm, gym, go, ip, sH, i_ch, g.H, g.W, gip, gi_ch, ggq, ggrid.s3, cy, queue);
         else
-            row_body<CS, kGin, kGgrid, true>(lane, col_ok, live, ix, iy, gxm, gym, go, ip, sH, i_ch, g.H, g.W, gip, gi_ch, ggq, ggrid.s3, cy, queue);
+            row_body<T, CS, kGin, kGgrid, true>(lane, col_ok, live, ix, iy, gxm, gym, go, ip, sH, i_ch, g.H, g.W, gip, gi_ch, ggq, ggrid.s3, cy, queue);
         if (kGgrid) ggq += ggrid.s1;
     }
     if (kGin && cy.live) {
@@ -191,25 +193,25 @@ bwd_lean_kernel(const View gout, const View in, const View grid, const View gin,
     }
 }
 
-template <int CS, bool kBorder, bool kAlign>
+template <typename T, int CS, bool kBorder, bool kAlign>
 void launch_ba(const Problem &pb, dim3 blocks, int n0, cudaStream_t st)
 {
     if (pb.want_gin && pb.want_ggrid)
-        { bwd_lean_kernel<CS, kBorder, kAlign, true, true><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, n0); note_launch(); }
+        { bwd_lean_kernel<T, CS, kBorder, kAlign, true, true><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, n0); note_launch(); }
     else if (pb.want_gin)
-        { bwd_lean_kernel<CS, kBorder, kAlign, true, false><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, n0); note_launch(); }
+        { bwd_lean_kernel<T, CS, kBorder, kAlign, true, false><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, n0); note_launch(); }
     else
-        { bwd_lean_kernel<CS, kBorder, kAlign, false, true><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, n0); note_launch(); }
+        { bwd_lean_kernel<T, CS, kBorder, kAlign, false, true><<<blocks, kThreads, 0, st>>>(pb.gout, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, n0); note_launch(); }
 }
 
-template <int CS>
+template <typename T, int CS>
 void launch_cs(const Problem &pb, dim3 blocks, int n0, cudaStream_t st)
 {
     const bool border = pb.g.padding == PWS_PAD_BORDER, align = pb.g.align != 0;
-    if (border && align) launch_ba<CS, true, true>(pb, blocks, n0, st);
-    else if (border) launch_ba<CS, true, false>(pb, blocks, n0, st);
-    else if (align) launch_ba<CS, false, true>(pb, blocks, n0, st);
-    else launch_ba<CS, false, false>(pb, blocks, n0, st);
+    if (border && align) launch_ba<T, CS, true, true>(pb, blocks, n0, st);
+    else if (border) launch_ba<T, CS, true, false>(pb, blocks, n0, st);
+    else if (align) launch_ba<T, CS, false, true>(pb, blocks, n0, st);
+    else launch_ba<T, CS, false, false>(pb, blocks, n0, st);
 }
 
 }  // namespace
@@ -217,7 +219,8 @@ void launch_cs(const Problem &pb, dim3 blocks, int n0, cudaStream_t st)
 bool backward_lean_eligible(const Problem &pb)
 {
     const Geometry &g = pb.g;
-    if (pb.in_dtype != PWS_F32 || pb.grid_dtype != PWS_F32) return false;
+    if (pb.grid_dtype != PWS_F32) return false;
+    if (pb.in_dtype != PWS_F32 && pb.in_dtype != PWS_F16 && pb.in_dtype != PWS_BF16) return false;
     if (g.C != 1 && g.C != 3) return false;
     if (pb.in.s3 != 1 || pb.gout.s3 != 1) return false;
     // the scatter reuses the frame's in-plane offset for grad_input: same pitch required
@@ -238,8 +241,9 @@ void launch_backward_lean(const Problem &pb, int n0, int nn, cudaStream_t st)
     for (int z0 = 0; z0 < nn; z0 += 65535) {
         const int nz = nn - z0 < 65535 ? nn - z0 : 65535;
         dim3 blocks((g.Wo + kTW - 1) / kTW, (g.Ho + kTH - 1) / kTH, nz);
-        if (g.C == 3) launch_cs<3>(pb, blocks, n0 + z0, st);
-        else launch_cs<1>(pb, blocks, n0 + z0, st);
+        if (pb.in_dtype == PWS_F32) { if (g.C == 3) launch_cs<float, 3>(pb, blocks, n0 + z0, st); else launch_cs<float, 1>(pb, blocks, n0 + z0, st); }
+        else if (pb.in_dtype == PWS_F16) { if (g.C == 3) launch_cs<__half, 3>(pb, blocks, n0 + z0, st); else launch_cs<__half, 1>(pb, blocks, n0 + z0, st); }
+        else { if (g.C == 3) launch_cs<__nv_bfloat16, 3>(pb, blocks, n0 + z0, st); else launch_cs<__nv_bfloat16, 1>(pb, blocks, n0 + z0, st); }
     }
 }
 

@@ -31,19 +31,21 @@ _INTERP = {"bilinear": 0, "nearest": 1, "bicubic": 2}
 _PADDING = {"zeros": 0, "border": 1, "reflection": 2}
 
 
-def _desc(t: torch.Tensor) -> _lib.PwsTensor:
-    d = _lib.PwsTensor()
-    d.data = t.data_ptr()
-    d.dtype = _DTYPES[t.dtype]
-    d.device = t.device.index if t.device.index is not None else torch.cuda.current_device()
-    for i in range(4):
-        d.size[i] = t.size(i)
-        d.stride[i] = t.stride(i)
-    return d
+_I64x10 = ctypes.c_int64 * 10
 
 
-def _stream(t: torch.Tensor) -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+def _desc(t: torch.Tensor):
+    """A pws_tensor for `t`, laid out by hand: {void *data; int32 dtype; int32 device; int64 size[4]; int64 stride[4]} is ten
+    little-endian 64-bit words, and ONE ctypes array construction is several times cheaper than filling a Structure field
+    by field -- the per-call host cost is what the 256 x 256 training shapes are bound by."""
+    dev = t.device.index
+    if dev is None:
+        dev = torch.cuda.current_device()
+    return _I64x10(t.data_ptr(), _DTYPES[t.dtype] | (dev << 32), *t.shape, *t.stride())
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
 
 
 def _require_cuda(input: torch.Tensor, grid: torch.Tensor) -> None:
@@ -81,10 +83,10 @@ def warp2d_forward(input: torch.Tensor, grid: torch.Tensor, padding: int, align_
     N, C = input.size(0), input.size(1)
     if out is None:
         out = torch.empty((N, C, grid.size(1), grid.size(2)), dtype=input.dtype, device=input.device)
-    with torch.cuda.device_of(input):
-        rc = lib.pws_warp2d_forward(ctypes.byref(_desc(input)), ctypes.byref(_desc(grid)), ctypes.byref(_desc(out)),
-                                    0, padding, int(align_corners), _stream(input))
-    _lib.check(rc)
+    # (no device context here: the library selects the tensors' device itself and restores the caller's)
+    rc = lib.pws_warp2d_forward(_desc(input), _desc(grid), _desc(out), 0, padding, int(align_corners), _stream(input))
+    if rc:
+        _lib.check(rc)
     return out
 
 
@@ -107,20 +109,25 @@ def warp2d_backward(grad_output: torch.Tensor, input: torch.Tensor, grid: torch.
     """aten::grid_sampler_2d_backward replacement. Returns (grad_input | None, grad_grid | None);
     caller-provided buffers are filled when given (grad_input need not be zeroed)."""
     lib = _lib.load()
-    if grid.dtype != input.dtype:
-        raise NotImplementedError("pwstablenet_b200: backward needs the map in the frame's dtype")
+    half_frames = grid.dtype != input.dtype      # 16-bit frames with an fp32 map (BASELINE config 5)
     gin = ggrid = None
     if output_mask[0]:
-        gin = grad_input if grad_input is not None else torch.empty(input.size(), dtype=input.dtype, device=input.device)
+        if half_frames:
+            # contributions are summed in fp32 and rounded to the frame type ONCE (a bf16 atomic would round after every add)
+            if grad_input is not None and grad_input.dtype != torch.float32:
+                raise RuntimeError("pwstablenet_b200: with 16-bit frames a caller-provided grad_input must be the fp32 accumulation buffer")
+            gin = grad_input if grad_input is not None else torch.empty(input.size(), dtype=torch.float32, device=input.device)
+        else:
+            gin = grad_input if grad_input is not None else torch.empty(input.size(), dtype=input.dtype, device=input.device)
     if output_mask[1]:
         ggrid = grad_grid if grad_grid is not None else _like_layout(grid)
-    with torch.cuda.device_of(input):
-        rc = lib.pws_warp2d_backward(
-            ctypes.byref(_desc(grad_output)), ctypes.byref(_desc(input)), ctypes.byref(_desc(grid)),
-            ctypes.byref(_desc(gin)) if gin is not None else None,
-            ctypes.byref(_desc(ggrid)) if ggrid is not None else None,
-            0, padding, int(align_corners), _stream(input))
-    _lib.check(rc)
+    rc = lib.pws_warp2d_backward(_desc(grad_output), _desc(input), _desc(grid),
+                                 _desc(gin) if gin is not None else None, _desc(ggrid) if ggrid is not None else None,
+                                 0, padding, int(align_corners), _stream(input))
+    if rc:
+        _lib.check(rc)
+    if half_frames and gin is not None and grad_input is None:
+        gin = gin.to(input.dtype)
     return gin, ggrid
 
 
@@ -177,8 +184,8 @@ def warp_taps(grid: torch.Tensor, in_h: int, in_w: int, padding_mode: str = "zer
     y0 = torch.empty_like(x0)
     mask = torch.empty((N, Ho, Wo), dtype=torch.uint8, device=grid.device)
     wts = torch.empty((N, Ho, Wo, 4), dtype=torch.float32, device=grid.device) if want_weights else None
-    with torch.cuda.device_of(grid):
-        rc = lib.pws_warp2d_taps(ctypes.byref(_desc(grid)), in_h, in_w, x0.data_ptr(), y0.data_ptr(), mask.data_ptr(),
+    if True:
+        rc = lib.pws_warp2d_taps(_desc(grid), in_h, in_w, x0.data_ptr(), y0.data_ptr(), mask.data_ptr(),
                                  wts.data_ptr() if wts is not None else None, _PADDING[padding_mode],
                                  int(align_corners), _stream(grid))
     _lib.check(rc)

@@ -202,3 +202,33 @@ def test_tma_forward_16bit_frames_fp32_maps(pw, dtype, pad):
                     assert out.dtype == dtype
                     ref = torch.ops.aten.grid_sampler_2d(f16.float(), g, 0, PAD[pad], align).to(dtype)
                     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+@pytest.mark.parametrize("shape", [(2, 3, 270, 480), (1, 3, 2160, 3840), (2, 1, 96, 160)])
+def test_backward_16bit_frames_fp32_maps(pw, dtype, pad, shape):
+    # BASELINE config 5 ("4K warp, bf16 frames with fp32 maps, zeros and border padding"), backward: torch rejects the dtype
+    # mix, so the oracle is the fp32 backward on the UPCAST frame and grad_output -- grad_grid bit-exact against this
+    # library's own fp32 path, <= 1e-5 against ATen; grad_input accumulated in fp32 (<= 1e-4 against ATen) and rounded to the
+    # frame type once
+    N, C, H, W = shape
+    frames, g, gout = make("smooth", N, C, H, W, H, W, False, "planar", seed=61)
+    f16, go16 = frames.to(dtype), gout.to(dtype)
+    gin, gg = pw.warp2d_backward(go16, f16, g, PAD[pad], False, (True, True))
+    assert last_kernel() == "bwd_lean_16"
+    assert gin.dtype == dtype and gg.dtype == torch.float32
+    rin, rg = pw.warp2d_backward(go16.float(), f16.float(), g, PAD[pad], False, (True, True))
+    assert torch.equal(gg, rg)
+    ain, ag = torch.ops.aten.grid_sampler_2d_backward(go16.float(), f16.float(), g, 0, PAD[pad], False, (True, True))
+    assert float((gg - ag).abs().max()) <= 1e-5 * float(ag.abs().max())
+    acc = torch.empty(f16.shape, dtype=torch.float32, device="cuda")
+    pw.warp2d_backward(go16, f16, g, PAD[pad], False, (True, False), grad_input=acc)
+    assert float((acc - ain).abs().max()) <= 1e-4 * float(ain.abs().max())
+    assert float((gin.float() - ain).abs().max()) <= (2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -10) * float(ain.abs().max()) * 1.01
+    # through autograd, as a user would call it
+    fa = f16.clone().requires_grad_(True)
+    ga = g.clone().requires_grad_(True)
+    out = pw.grid_sample(fa, ga, "bilinear", pad, False)
+    out.backward(go16)
+    assert fa.grad.dtype == dtype and torch.equal(ga.grad, gg)

@@ -42,7 +42,7 @@ def test_netg_gradients_through_install_equal_stock_torch(setup):
         from pwstablenet_b200 import _lib
         l0 = _lib.launch_count()
         g_pw, l_pw = T.grads_of(net, batch)
-        assert _lib.launch_count() - l0 >= 22, "the warps did not go through libpwswarp"      # 11 forward + 11 backward
+        assert _lib.launch_count() - l0 == 20, "the warps did not go through libpwswarp"      # 11 forward + 9 backward (the gray warps feed no loss term: SURVEY 3.1)
         g_fused, l_fused = T.grads_of(net, batch, fused=True)
     finally:
         pw.uninstall()

@@ -156,7 +156,7 @@ def grads_of(netG, batch, vgg=None, fused=False):
         p.grad = None
     loss_g, _ = forward_losses(netG, batch, vgg, fused)
     loss_g.backward()
-    return torch.cat([p.grad.reshape(-1) for p in netG.parameters()]), float(loss_g)
+    return torch.cat([p.grad.reshape(-1) for p in netG.parameters()]), float(loss_g.detach())
 
 
 def standalone_warps(batch_n, device, reps=5):
