@@ -167,6 +167,17 @@ int launch_stages_forward(const View &in, const StageViews &sv, int K, const Geo
 int launch_stages_backward(const View &in, const StageViews &sv, int K, const View &gin, bool want_gin, const Geometry &g,
                            const StageScale &sc, cudaStream_t st);
 
+// Calls whose whole working set sits in L2 (the reference's training shapes: 16 x 3 x 256 x 256 = 12.6 MB) are bound by the
+// launch, not by HBM: they take the plain one-wave kernels (no tensor maps to encode, no counter slot to lease, no
+// 227 KB persistent CTAs to set up) instead of the TMA pipelines.
+#ifndef PWS_SMALL_ELEMS
+#define PWS_SMALL_ELEMS (4 << 20)   // output elements (16 MB of fp32)
+#endif
+inline bool small_problem(const Problem &pb)
+{
+    return (int64_t)pb.g.N * pb.g.C * pb.g.Ho * pb.g.Wo <= (int64_t)PWS_SMALL_ELEMS;
+}
+
 int launch_forward(const Problem &pb, cudaStream_t st);
 int launch_backward(const Problem &pb, cudaStream_t st);
 int launch_taps(const View &grid, const Geometry &g, int32_t *x0, int32_t *y0, uint8_t *mask, float *w, cudaStream_t st);

@@ -226,7 +226,7 @@ int launch_typed(const Problem &pb, cudaStream_t st)
         if (per_chunk > g.N) per_chunk = g.N;
     }
     const bool lean = sizeof(T) == 4 && !force_generic() && backward_lean_eligible(pb);
-    BwdTmaPlan *plan = (sizeof(T) == 4 && !force_generic()) ? backward_tma_plan(pb) : nullptr;
+    BwdTmaPlan *plan = (sizeof(T) == 4 && !force_generic() && !(lean && small_problem(pb))) ? backward_tma_plan(pb) : nullptr;
     struct PlanGuard { BwdTmaPlan *p; ~PlanGuard() { if (p) backward_tma_free(p); } } plan_guard{plan};
     const int cs = (g.C == 3) ? 3 : (g.C % 4 == 0) ? 4 : (g.C % 2 == 0) ? 2 : 1;
     if (plan) {

@@ -58,15 +58,18 @@ constexpr int kSyncSlots = kLaunchSlots, kSyncFrames = 256;
 // The zero-fill is tracked in bands of 1/8 frame (rows [ceil(b*H/8), ceil((b+1)*H/8)) of every channel plane): a tile
 // only needs the bands its taps can reach.  (Measured: with band tracking the best look-ahead is still 3-4 bands --
 // 0.593 / 0.482 / 0.469 / 0.468 ms at 1 / 2 / 3 / 4 -- so the finer grain buys robustness, not speed.)
-constexpr int kBands = 8;
-__device__ unsigned int g_zero_done[kSyncSlots][kSyncFrames * kBands];
+// Every band costs its CTA's zero-fill warp a fence, an atomic and a poll (~1 us): a launch of many SMALL frames must not pay
+// eight of them per frame, so the number of bands per frame follows the frame size (about 2 MB of grad_input per band,
+// 1..kMaxBands).
+constexpr int kMaxBands = 8;
+__device__ unsigned int g_zero_done[kSyncSlots][kSyncFrames * kMaxBands];
 __device__ unsigned int g_exit_count[kSyncSlots];
 // Tiles are handed out dynamically: the SMs of a B200 do not run this kernel at the same pace (the spread is several
 // per cent: distance to the L2 slices, neighbours on the same TPC), and with a static round-robin every frame ended
 // with the fast CTAs waiting at the zero-fill counter of the next frame for the slow ones.
 __device__ unsigned int g_tile_next[kSyncSlots];
 // (slots are leased per device and reused only after their previous launch has finished: pws_launch.cuh)
-// how far the zero-fill runs ahead of the scatter, in eighths of a frame
+// how far the zero-fill runs ahead of the scatter, in bands
 constexpr int kZeroAhead = 4;
 
 // the scouts' progress words: a flag polled by the zero-fill warp, not data
@@ -359,6 +362,10 @@ __device__ __forceinline__ void interior_strip(
     float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Queue<CS> &q, const uint64_t pol_first)
 {
     constexpr int kPitch = box_w(SHAPE), kPlane = box_w(SHAPE) * box_h(SHAPE);
+    // The two scatter refinements trade ~16 issue slots per row for a quarter fewer queue entries.  The grad_input-only kernel
+    // is bound by the RED path and has issue slots to spare (0.383 -> 0.367 ms / 16 1080p frames); the kernel that also
+    // computes grad_grid is issue-bound and loses what the RED path gains (0.469 -> 0.474): it keeps the plain scheme.
+    constexpr bool kEcarry = PWS_BWD_ECARRY && !kGgrid, kVdup = PWS_BWD_VDUP && !kGgrid;
     const unsigned lt = (1u << lane) - 1u;
     int co = -1, eo = -1;        // linear offsets of the parked south-west / south-east sums' targets; -1: nothing parked
     float cv[CS], ev[CS];
@@ -410,10 +417,10 @@ __device__ __forceinline__ void interior_strip(
             const bool given = ((__ballot_sync(0xffffffffu, take) >> 1) >> lane) & 1u;
             // (r > 0: nothing is parked in the strip's first row; the loop is unrolled, the test is free)
             const bool chain = r > 0 && co == o;                           // the parked south-west sum lands on this row's north-west tap
-            const bool vdup = r > 0 && PWS_BWD_VDUP && co == o + W;        // ... on its south-west tap: same source row again
+            const bool vdup = r > 0 && kVdup && co == o + W;        // ... on its south-west tap: same source row again
             const bool broke = r > 0 && !chain && !vdup;
-            const bool e_chain = r > 0 && PWS_BWD_ECARRY && eo == o + 1, e_vdup = r > 0 && PWS_BWD_ECARRY && PWS_BWD_VDUP && eo == o + W + 1;
-            const bool e_broke = r > 0 && PWS_BWD_ECARRY && eo >= 0 && !e_chain && !e_vdup;
+            const bool e_chain = r > 0 && kEcarry && eo == o + 1, e_vdup = r > 0 && kEcarry && kVdup && eo == o + W + 1;
+            const bool e_broke = r > 0 && kEcarry && eo >= 0 && !e_chain && !e_vdup;
             const float2 ns = make_float2(dn, ds);
             const float2 w_w = x2::mul(x2::bc(dw), ns), w_e = x2::mul(x2::bc(de), ns);   // (nw, sw), (ne, se)
             float et[CS], eb[CS], old_c[CS], old_e[CS];
@@ -437,24 +444,24 @@ __device__ __forceinline__ void interior_strip(
             }
             // stragglers -> queue: the north-east tap nobody took, parked sums whose chain broke
             queue_push<CS>(q, !given, o + 1, et, lt, gp, lane);
-            if (!PWS_BWD_ECARRY) queue_push<CS>(q, !given, o + W + 1, eb, lt, gp, lane);
+            if (!kEcarry) queue_push<CS>(q, !given, o + W + 1, eb, lt, gp, lane);
             queue_push<CS>(q, broke, co, old_c, lt, gp, lane);
-            if (PWS_BWD_ECARRY) queue_push<CS>(q, e_broke, eo, old_e, lt, gp, lane);
+            if (kEcarry) queue_push<CS>(q, e_broke, eo, old_e, lt, gp, lane);
             co = o + W;
-            eo = (PWS_BWD_ECARRY && !given) ? o + W + 1 : -1;
+            eo = (kEcarry && !given) ? o + W + 1 : -1;
         }
     }
     if (kGin) {
 #pragma unroll
         for (int k = 0; k < CS; ++k) PWS_RED(at(gp[k], co), cv[k]);   // every lane parked a south-west sum in the last row
-        if (PWS_BWD_ECARRY) queue_push<CS>(q, eo >= 0, eo, ev, lt, gp, lane);
+        if (kEcarry) queue_push<CS>(q, eo >= 0, eo, ev, lt, gp, lane);
     }
 }
 
 template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 __global__ void __launch_bounds__(kThreads, 1)
 bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View grid, const View gin, const View ggrid, const Geometry g,
-               const int tiles_x, const int tiles_y, const int total_tiles, const int n_begin, const int n_frames, const int slot)
+               const int tiles_x, const int tiles_y, const int total_tiles, const int n_begin, const int n_frames, const int slot, const int kBands)
 {
     using S = Smem<CS, kGgrid>;
     constexpr int kStages = S::kStages, kMapStages = S::kMapStages;
@@ -468,7 +475,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     uint64_t *const empty = full + kStages;
     uint64_t *const map_full = empty + kStages;
     uint64_t *const map_empty = map_full + kMapStages;
-    // [0], [1] per scout: how far it has dispatched, in eighths of a frame; [2]: the last band (8 * frame + band) known
+    // [0], [1] per scout: how far it has dispatched, in bands; [2]: the last band (8 * frame + band) known
     // to be zero-filled by every CTA, published by the zero-fill warp.  Written by the scouts and polled by the zero-fill
     // warp (volatile; compute-sanitizer's racecheck flags exactly this pair and nothing else -- build with
     // -DPWS_BWD_ATOMIC_PROGRESS to run it clean)
@@ -552,7 +559,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             if (kGgrid && kSlotShape < kNumShapes - 1 && !(info.z & (kInfoFallback | kInfoEmpty)) && (info.z & 0xff) > kSlotShape)
                 info = make_int4(0, 0, kInfoFallback, 0);
             info.w = tc.n;
-            const int progress = 8 * tc.n + (8 * (t - tc.n * tiles_xy)) / tiles_xy;  // in eighths of a frame
+            const int progress = kBands * tc.n + (kBands * (t - tc.n * tiles_xy)) / tiles_xy;  // in bands
             const bool want_box = kGgrid && !(info.z & (kInfoFallback | kInfoEmpty));
             const int shape = info.z & 0xff;
             tma::mbar_wait_relaxed(empty + st, ph ^ 1);
@@ -695,6 +702,9 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
     SlotLease lease(kRingBackward, st);
     if (!lease.ok()) return false;  // stream capture: the caller takes the memset + non-persistent kernel path
     int slot = lease.slot();
+    const int64_t frame_bytes = (int64_t)CS * pb.g.H * pb.g.W * 4;
+    int bands = (int)((frame_bytes + (2 << 20) - 1) / (2 << 20));
+    bands = bands < 1 ? 1 : bands > kMaxBands ? kMaxBands : bands;
     // The scouts wait for EVERY CTA of the launch to have zero-filled a band of grad_input: all CTAs must be resident at
     // the same time.  A cooperative launch makes the driver guarantee that (or refuse the launch: SM-limited contexts
     // such as MPS partitions or green contexts, where the caller then falls back to the non-persistent kernels).
@@ -703,7 +713,7 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, kern, tp, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0, n_frames, slot) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, kern, tp, pb.in, pb.grid, pb.gin, pb.ggrid, pb.g, tiles_x, tiles_y, total, n0, n_frames, slot, bands) != cudaSuccess) {
         cudaGetLastError();
         lease.cancel();
         return false;

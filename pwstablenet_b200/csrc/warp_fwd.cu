@@ -137,6 +137,7 @@ static bool force_direct()
 
 int launch_forward(const Problem &pb, cudaStream_t st)
 {
+    if (!force_direct() && small_problem(pb) && launch_forward_tile(pb, st)) { note_kernel("fwd_lean"); return PWS_OK; }
     if (!force_direct() && launch_forward_tma(pb, st)) return PWS_OK;
     if (!force_direct() && launch_forward_tile(pb, st)) { note_kernel("fwd_lean"); return PWS_OK; }
     note_kernel("fwd_direct");

@@ -97,3 +97,29 @@ g = maps("smooth", N, H, W)
 for pad, pname in ((0, "zeros"), (1, "border")):
     ms = t(lambda: pw.warp2d_forward(fr, g, pad, False), 5, 2); k = _lib.last_kernel()
     row(f"config 5: 8x3x2160x3840 bf16 frames, fp32 maps, {pname}, forward (20 B/px)", ms, 20 * N * H * W, N, k)
+go16 = torch.rand(N, C, H, W, device="cuda").to(torch.bfloat16)
+for pad, pname in ((0, "zeros"), (1, "border")):
+    ms = t(lambda: pw.warp2d_backward(go16, fr, g, pad, False, (True, True)), 3, 1); k = _lib.last_kernel()
+    # bf16 grad_out + fp32 map + bf16 frame read, fp32 grad_grid written, grad_input written once (fp32 buffer) + rounded copy
+    row(f"config 5: same, backward (both gradients), {pname} (34 B/px)", ms, 34 * N * H * W, N, k)
+del fr, g, go16
+# the cascade's call-site fusion: three maps, one frame, pre / post scale folded (R/main_new.py:103-107), 16x3x256x256
+N, C, H, W = 16, 3, 256, 256
+fr = torch.rand(N, C, H, W, device="cuda") * 2 - 1
+g3 = [maps("smooth", N, H, W) + 0.002 * i for i in range(3)]
+def ref_seq(sampler):
+    return [sampler((fr + 1) * 127.5, g) / 127.5 - 1 for g in g3]
+ms = t(lambda: pw.warp_stages(fr, g3, pre=(1.0, 127.5), post=(127.5, -1.0)), 50); k = _lib.last_kernel()
+aten_ms = t(lambda: ref_seq(lambda x, g: torch.ops.aten.grid_sampler_2d(x, g, 0, 0, False)), 50)
+row("config 3: three stage maps on one frame, (x+1)*127.5 .. /127.5-1 folded, forward (one launch)", ms, (3 * 4 + 3 * (8 + 12)) * N * H * W, N, k, aten_ms)
+gr3 = [g.clone().requires_grad_(True) for g in g3]
+gos = [torch.rand(N, C, H, W, device="cuda") for _ in range(3)]
+def fb(fn):
+    for g in gr3: g.grad = None
+    outs = fn()
+    torch.autograd.backward(list(outs), gos)
+ms = t(lambda: fb(lambda: pw.warp_stages(fr, gr3, pre=(1.0, 127.5), post=(127.5, -1.0))), 30); k = _lib.last_kernel()
+aten_ms = t(lambda: fb(lambda: [torch.ops.aten.grid_sampler_2d((fr + 1) * 127.5, g, 0, 0, False) / 127.5 - 1 for g in gr3]), 30)
+row("config 3: the same, forward + backward through autograd (grad to the three maps)", ms, (3 * 4 + 3 * (8 + 12) + 3 * 4 + 3 * (12 + 8 + 8)) * N * H * W, N, k, aten_ms)
+ours_ms = t(lambda: fb(lambda: [pw.grid_sample((fr + 1) * 127.5, g, "bilinear", "zeros", False) / 127.5 - 1 for g in gr3]), 30)
+print(f"| (the same through three pw.grid_sample calls + torch elementwise ops: {ours_ms:.3f} ms) | | | | | | |")
