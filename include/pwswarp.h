@@ -84,6 +84,13 @@ uint64_t pws_launch_count(void);
  * ("fwd_tma", "fwd_lean", "fwd_direct", "bwd_tma", "bwd_lean", "bwd_march", "fused", ...; "" before any call). */
 const char *pws_last_kernel(void);
 
+/* Tuning knob (process-wide, like a library's "benchmark" switch; results do not depend on it): calls whose output has at
+ * most this many elements -- the whole working set sits in L2, the call is bound by its launch -- take the plain one-wave
+ * kernels instead of the persistent TMA pipelines.  Returns the previous value; a negative argument only queries.
+ * Default 4 Mi elements (the reference's 16 x 3 x 256 x 256 training shapes are 3 Mi).  0 = always the TMA pipelines
+ * (the test-suite uses that to reach them with small inputs). */
+int64_t pws_small_problem_elems(int64_t elems);
+
 /* out[n,c,h,w] = sum over the 4 bilinear taps of in[n,c,y_tap,x_tap] * w_tap,
  * replaces aten::grid_sampler_2d for interp = bilinear, padding in {zeros, border}.
  * Frame dtype: f32, f16, bf16, f64.  Map dtype: the frame's dtype or f32 (an

@@ -17,6 +17,7 @@ EXPORTS = (
     "pws_last_error",
     "pws_launch_count",
     "pws_last_kernel",
+    "pws_small_problem_elems",
     "pws_warp2d_forward",
     "pws_warp2d_backward",
     "pws_warp2d_taps",
@@ -78,6 +79,8 @@ def load() -> ctypes.CDLL:
     lib.pws_last_error.restype = ctypes.c_char_p
     lib.pws_launch_count.restype = ctypes.c_uint64
     lib.pws_last_kernel.restype = ctypes.c_char_p
+    lib.pws_small_problem_elems.restype = ctypes.c_int64
+    lib.pws_small_problem_elems.argtypes = [ctypes.c_int64]
     lib.pws_warp2d_forward.restype = ctypes.c_int
     lib.pws_warp2d_forward.argtypes = [P, P, P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.pws_warp2d_backward.restype = ctypes.c_int
@@ -112,6 +115,12 @@ def launch_count() -> int:
 def last_kernel() -> str:
     """Kernel family the last forward / backward call on this thread launched (debug / tests)."""
     return load().pws_last_kernel().decode("ascii", "replace")
+
+
+def small_problem_elems(elems: int = -1) -> int:
+    """Query (negative argument) or set the output-element threshold below which calls take the one-wave kernels; returns
+    the previous value (include/pwswarp.h)."""
+    return int(load().pws_small_problem_elems(int(elems)))
 
 
 def last_error() -> str:

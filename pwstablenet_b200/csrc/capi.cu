@@ -14,6 +14,8 @@ static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 
 static thread_local const char *g_last_kernel = "";
+static std::atomic<int64_t> g_small_elems{(int64_t)PWS_SMALL_ELEMS};
+int64_t small_problem_threshold() { return g_small_elems.load(std::memory_order_relaxed); }
 void note_launch(int kernels) { g_launches.fetch_add((uint64_t)kernels, std::memory_order_relaxed); }
 void note_kernel(const char *family) { g_last_kernel = family; }
 
@@ -217,6 +219,12 @@ __attribute__((visibility("default"))) const char *pws_last_error(void) { return
 __attribute__((visibility("default"))) uint64_t pws_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 __attribute__((visibility("default"))) const char *pws_last_kernel(void) { return g_last_kernel; }
+
+__attribute__((visibility("default"))) int64_t pws_small_problem_elems(int64_t elems)
+{
+    if (elems < 0) return g_small_elems.load(std::memory_order_relaxed);
+    return g_small_elems.exchange(elems, std::memory_order_relaxed);
+}
 
 __attribute__((visibility("default")))
 int pws_warp2d_forward(const pws_tensor *in, const pws_tensor *grid, pws_tensor *out,

@@ -171,11 +171,12 @@ int launch_stages_backward(const View &in, const StageViews &sv, int K, const Vi
 // launch, not by HBM: they take the plain one-wave kernels (no tensor maps to encode, no counter slot to lease, no
 // 227 KB persistent CTAs to set up) instead of the TMA pipelines.
 #ifndef PWS_SMALL_ELEMS
-#define PWS_SMALL_ELEMS (4 << 20)   // output elements (16 MB of fp32)
+#define PWS_SMALL_ELEMS (4 << 20)   // output elements (16 MB of fp32): default of pws_small_problem_elems()
 #endif
+int64_t small_problem_threshold();   // capi.cu
 inline bool small_problem(const Problem &pb)
 {
-    return (int64_t)pb.g.N * pb.g.C * pb.g.Ho * pb.g.Wo <= (int64_t)PWS_SMALL_ELEMS;
+    return (int64_t)pb.g.N * pb.g.C * pb.g.Ho * pb.g.Wo <= small_problem_threshold();
 }
 
 int launch_forward(const Problem &pb, cudaStream_t st);

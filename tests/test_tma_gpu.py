@@ -23,7 +23,10 @@ def pw():
     import pwstablenet_b200 as pw
     from pwstablenet_b200 import _lib
     _lib.load()
-    return pw
+    # this module is about the persistent TMA kernels: reach them with small inputs too (pws_small_problem_elems)
+    prev = _lib.small_problem_elems(0)
+    yield pw
+    _lib.small_problem_elems(prev)
 
 
 def last_kernel():
