@@ -341,6 +341,23 @@ __device__ __forceinline__ void queue_push(Queue<CS> &q, const bool p, const int
     }
 }
 
+// two entries per flagged lane (the untaken north-east and south-east taps): one vote serves both
+template <int CS>
+__device__ __forceinline__ void queue_push2(Queue<CS> &q, const bool p, const int off_a, const float (&a)[CS], const int off_b,
+                                            const float (&b)[CS], const unsigned lt, float *const (&gp)[CS], const int lane)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if (m) {
+        const int n = __popc(m), rank = __popc(m & lt);
+        if (p) queue_put<CS>(q, q.count + rank, off_a, a);
+        q.count += n;
+        if (q.count >= 32) queue_drain<CS>(q, gp, lane);
+        if (p) queue_put<CS>(q, q.count + rank, off_b, b);
+        q.count += n;
+        if (q.count >= 32) queue_drain<CS>(q, gp, lane);
+    }
+}
+
 // A strip (32 pixels x kStripRows rows) of an INTERIOR tile: the tile is full and every tap of every pixel lies inside
 // the frame, so there are no masks, the floor is one round-down add (floor_small), and a source pixel is identified by its
 // linear offset alone.  The arithmetic runs on fp32 PAIRS (pws_f32x2.cuh) wherever two independent chains exist:
@@ -362,6 +379,9 @@ __device__ __forceinline__ void interior_strip(
     float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Queue<CS> &q, const uint64_t pol_first)
 {
     constexpr int kPitch = box_w(SHAPE), kPlane = box_w(SHAPE) * box_h(SHAPE);
+    // the two grad_grid stores of a pixel: running byte pointers, one 64-bit add each per row
+    char *gq_x = reinterpret_cast<char *>(ggq), *gq_y = reinterpret_cast<char *>(ggq + gg_s3);
+    const int64_t gq_step = (int64_t)gg_s1 * 4;
     // The two scatter refinements trade ~16 issue slots per row for a quarter fewer queue entries.  The grad_input-only kernel
     // is bound by the RED path and has issue slots to spare (0.383 -> 0.367 ms / 16 1080p frames); the kernel that also
     // computes grad_grid is issue-bound and loses what the RED path gains (0.469 -> 0.474): it keeps the plain scheme.
@@ -404,8 +424,10 @@ __device__ __forceinline__ void interior_strip(
                 acc = x2::fma(x2::mul(x2::bc(v3), c_se), g2, acc);
             }
             acc = x2::mul(gmul2, acc);
-            tma::st_f32_hint(ggq, acc.y, pol_first); tma::st_f32_hint(ggq + gg_s3, acc.x, pol_first);
-            ggq += gg_s1;
+            tma::st_f32_hint(reinterpret_cast<float *>(gq_x), acc.y, pol_first); tma::st_f32_hint(reinterpret_cast<float *>(gq_y), acc.x, pol_first);
+            // (volatile: the unrolled rows otherwise recompute base + r * step with twice the 64-bit adds)
+            asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_x) : "l"(gq_step));
+            asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_y) : "l"(gq_step));
         }
 
         if (kGin) {
@@ -421,30 +443,28 @@ __device__ __forceinline__ void interior_strip(
             const bool broke = r > 0 && !chain && !vdup;
             const bool e_chain = r > 0 && kEcarry && eo == o + 1, e_vdup = r > 0 && kEcarry && kVdup && eo == o + W + 1;
             const bool e_broke = r > 0 && kEcarry && eo >= 0 && !e_chain && !e_vdup;
-            const float2 ns = make_float2(dn, ds);
-            const float2 w_w = x2::mul(x2::bc(dw), ns), w_e = x2::mul(x2::bc(de), ns);   // (nw, sw), (ne, se)
+            // (scalar: pairs would need as many register moves here as they save multiplies)
+            const float nw = fmul(dw, dn), ne = fmul(de, dn), sw = fmul(dw, ds), se = fmul(de, ds);
             float et[CS], eb[CS], old_c[CS], old_e[CS];
 #pragma unroll
             for (int k = 0; k < CS; ++k) {
-                const float2 g2 = x2::bc(go[k]);
-                float2 tb = x2::mul(w_w, g2);               // (top, bottom) of the west column
-                const float2 e2 = x2::mul(w_e, g2);         // ... of the east column
-                et[k] = e2.x; eb[k] = e2.y;
+                float top = fmul(nw, go[k]), bot = fmul(sw, go[k]);   // west column
+                et[k] = fmul(ne, go[k]); eb[k] = fmul(se, go[k]);     // east column
                 old_e[k] = ev[k];
                 if (e_chain) et[k] += ev[k];                // parked south-east sum: this row's north-east tap
                 if (e_vdup) eb[k] += ev[k];
-                const float2 pe = make_float2(__shfl_up_sync(0xffffffffu, et[k], 1), __shfl_up_sync(0xffffffffu, eb[k], 1));
-                if (take) tb = x2::add(tb, pe);
+                const float pt = __shfl_up_sync(0xffffffffu, et[k], 1), pb = __shfl_up_sync(0xffffffffu, eb[k], 1);
+                if (take) { top += pt; bot += pb; }
                 old_c[k] = cv[k];
-                if (chain) tb.x += cv[k];
-                if (vdup) tb.y += cv[k];
-                PWS_RED(at(gp[k], o), tb.x);
-                cv[k] = tb.y;
+                if (chain) top += cv[k];
+                if (vdup) bot += cv[k];
+                PWS_RED(at(gp[k], o), top);
+                cv[k] = bot;
                 ev[k] = eb[k];
             }
             // stragglers -> queue: the north-east tap nobody took, parked sums whose chain broke
-            queue_push<CS>(q, !given, o + 1, et, lt, gp, lane);
-            if (!kEcarry) queue_push<CS>(q, !given, o + W + 1, eb, lt, gp, lane);
+            if (kEcarry) queue_push<CS>(q, !given, o + 1, et, lt, gp, lane);
+            else queue_push2<CS>(q, !given, o + 1, et, o + W + 1, eb, lt, gp, lane);
             queue_push<CS>(q, broke, co, old_c, lt, gp, lane);
             if (kEcarry) queue_push<CS>(q, e_broke, eo, old_e, lt, gp, lane);
             co = o + W;
