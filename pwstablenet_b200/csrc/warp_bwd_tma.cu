@@ -46,8 +46,28 @@ namespace {
 #define PWS_BWD_VDUP 1
 #endif
 constexpr int kScouts = 2, kGroups = 2, kGroupWarps = 8, kConsumers = kGroups * kGroupWarps;
-constexpr int kThreads = (kScouts + kConsumers + 1) * 32;  // scouts, consumers, the warp that zero-fills grad_input
-constexpr int kZeroWarp = kScouts + kConsumers;
+// The zero-fill of grad_input paces the whole kernel when ONE warp does it: a band costs that warp its stores plus a
+// gpu-scope fence (~2 us while the REDs keep the memory system busy), 128 bands of a 16-frame launch = the kernel's 0.46 ms
+// (ncu: the zero-fill warp never sleeps, half of its samples sit on the fence).  kZeroWarps warps take the bands round-robin.
+// interior strip form: 0 = two phases (grad_grid of all rows, then the scatter), 1 = fused rows with a run-time box pitch,
+// 2 = fused rows, one copy of the body per box shape (compile-time pitch)
+#ifndef PWS_BWD_STRIP
+#define PWS_BWD_STRIP 1
+#endif
+// pause of a zero-fill warp between two looks at the scouts' progress (a band lasts ~5 us; at 256 ns the polls were 7 % of
+// the kernel's instructions)
+#ifndef PWS_BWD_ZERO_POLL_NS
+#define PWS_BWD_ZERO_POLL_NS 1000
+#endif
+#ifndef PWS_BWD_L2PF
+#define PWS_BWD_L2PF 0   // measured: 0.434 -> 0.442 ms with it (the loads are not what the consumers wait for)
+#endif
+#ifndef PWS_BWD_ZERO_WARPS
+#define PWS_BWD_ZERO_WARPS 2
+#endif
+constexpr int kZeroWarps = PWS_BWD_ZERO_WARPS;
+constexpr int kThreads = (kScouts + kConsumers + kZeroWarps) * 32;  // scouts, consumers, the warps that zero-fill grad_input
+constexpr int kZeroWarp = kScouts + kConsumers;                      // first of them
 static_assert(kScouts == kGroups, "scout w feeds consumer group w (and tells it when the tiles have run out)");
 constexpr int kInfoStop = 1 << 11;  // info.z: no more tiles for this consumer group
 
@@ -59,7 +79,7 @@ constexpr int kSyncSlots = kLaunchSlots, kSyncFrames = 256;
 // only needs the bands its taps can reach.  (Measured: with band tracking the best look-ahead is still 3-4 bands --
 // 0.593 / 0.482 / 0.469 / 0.468 ms at 1 / 2 / 3 / 4 -- so the finer grain buys robustness, not speed.)
 // Every band costs its CTA's zero-fill warp a fence, an atomic and a poll (~1 us): a launch of many SMALL frames must not pay
-// eight of them per frame, so the number of bands per frame follows the frame size (about 2 MB of grad_input per band,
+// eight of them per frame, so the number of bands per frame follows the frame size (about 4 MB of grad_input per band,
 // 1..kMaxBands).
 constexpr int kMaxBands = 8;
 __device__ unsigned int g_zero_done[kSyncSlots][kSyncFrames * kMaxBands];
@@ -359,29 +379,145 @@ __device__ __forceinline__ void queue_push2(Queue<CS> &q, const bool p, const in
 }
 
 // A strip (32 pixels x kStripRows rows) of an INTERIOR tile: the tile is full and every tap of every pixel lies inside
-// the frame, so there are no masks, the floor is one round-down add (floor_small), and a source pixel is identified by its
-// linear offset alone.  The arithmetic runs on fp32 PAIRS (pws_f32x2.cuh) wherever two independent chains exist:
-//   coordinates  (x, y) through unnormalise / floor / fraction together;
-//   grad_grid    the accumulators (giy, gix) as one pair: per tap and channel one FMUL2 (tap value x the pair of
-//                fraction weights, sign folded into the weights: -(v*d) == v*(-d) exactly) and one FFMA2 with
-//                grad_output -- ATen's statements, operation for operation, so the result is bit-identical;
-//   grad_input   (north, south) weight pairs: (nw, sw) = dw * (dn, ds), (ne, se) = de * (dn, ds), the products with
-//                grad_output and the take-over add as pairs.
-// dw = 1 - de instead of (x0 + 1) - ix: de = ix - x0 is exact (Sterbenz), so both are the rounding of the same real
-// number 1 + x0 - ix.
-// SHAPE: the tile's box shape -- row pitch and plane size of the box are compile-time, the twelve taps of a pixel are
-// one address register plus immediates.
-template <int CS, bool kAlign, bool kInter, bool kGin, bool kGgrid, int SHAPE>
+// the frame, so there are no masks, the floor is one round-down add, and a source pixel is identified by its linear
+// offset alone.
+// The strip runs in TWO PHASES.  ncu showed the fused row body bound by latency, not by issue slots (45 % issue-active;
+// the top stalls inside the body were fixed-latency dependencies, LDS latency and instruction fetch): a row's grad_grid
+// is one dependent chain of 12 FMA pairs behind its tap loads, the scatter of the same row is a chain of shuffles, votes
+// and branches, and with four consumer warps per scheduler there is nobody to hide either.  Phase 1 computes grad_grid
+// of all the strip's rows -- no branches, fully unrolled: four independent chains for the scheduler to interleave;
+// phase 2 re-reads the map and grad_output from shared memory (15 cheap instructions per row) and runs the scatter.
+// Coordinates run on fp32 PAIRS (pws_f32x2.cuh); grad_grid accumulates (giy, gix) as one pair: per tap and channel one
+// FMUL2 (tap value x the pair of fraction weights, ATen's sign folded into the weights: -(v*d) == v*(-d) exactly) and one
+// FFMA2 with grad_output -- ATen's statements, operation for operation, so the result is bit-identical.
+// dw = 1 - de instead of (x0 + 1) - ix: de = ix - x0 is exact, so both are the rounding of the same real number.
+template <bool kAlign, bool kInter>
+__device__ __forceinline__ void strip_coords(const float *__restrict__ mq, const int r, const float2 size2,
+                                             int &x0, int &y0, float2 &es, float2 &wn)
+{
+    float2 gxy;
+    if (kInter) gxy = *reinterpret_cast<const float2 *>(mq + r * (2 * kTW));
+    else { gxy.x = mq[r * kTW]; gxy.y = mq[kTW * kTH + r * kTW]; }
+    // unnormalise (ATen's operation order), floor, fractions
+    const float2 t = x2::add(gxy, x2::bc(1.0f));
+    const float2 ixy = kAlign ? x2::mul(x2::mul(t, x2::bc(0.5f)), size2) : x2::mul(x2::fma(t, size2, x2::bc(-1.0f)), x2::bc(0.5f));
+    const float2 fl = x2::add_rm(ixy, x2::bc(12582912.0f));              // 1.5 * 2^23: the integer part lands in the mantissa
+    x0 = __float_as_int(fl.x) - 0x4B400000; y0 = __float_as_int(fl.y) - 0x4B400000;
+    es = x2::sub(ixy, x2::add(fl, x2::bc(-12582912.0f)));                // (de, ds) = (ix - x0, iy - y0)
+    wn = x2::sub(x2::bc(1.0f), es);                                      // (dw, dn)
+}
+
+template <int CS, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 __device__ __forceinline__ void interior_strip(
     const int lane, const float *__restrict__ mq /* this lane's map element(s) in the strip's first row */,
-    const float *__restrict__ gop, const float *__restrict__ bp,
+    const float *__restrict__ gop, const float *__restrict__ bp /* box base, origin folded in */, const int pitch, const int plane,
     const float2 size2 /* (W, H) as floats; (W-1, H-1) when kAlign */, const int W, const float2 gmul2 /* (gym, gxm) */,
     float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Queue<CS> &q, const uint64_t pol_first)
 {
-    constexpr int kPitch = box_w(SHAPE), kPlane = box_w(SHAPE) * box_h(SHAPE);
-    // the two grad_grid stores of a pixel: running byte pointers, one 64-bit add each per row
-    char *gq_x = reinterpret_cast<char *>(ggq), *gq_y = reinterpret_cast<char *>(ggq + gg_s3);
-    const int64_t gq_step = (int64_t)gg_s1 * 4;
+    // The two scatter refinements trade ~16 issue slots per row for a quarter fewer queue entries.  The grad_input-only kernel
+    // is bound by the RED path (0.383 -> 0.367 ms / 16 1080p frames); the kernel that also computes grad_grid gains nothing.
+    constexpr bool kEcarry = PWS_BWD_ECARRY && !kGgrid, kVdup = PWS_BWD_VDUP && !kGgrid;
+
+    if (kGgrid) {
+        // the two grad_grid stores of a pixel: running byte pointers, one 64-bit add each per row
+        char *gq_x = reinterpret_cast<char *>(ggq), *gq_y = reinterpret_cast<char *>(ggq + gg_s3);
+        const int64_t gq_step = (int64_t)gg_s1 * 4;
+#pragma unroll
+        for (int r = 0; r < kStripRows; ++r) {
+            int x0, y0; float2 es, wn;
+            strip_coords<kAlign, kInter>(mq, r, size2, x0, y0, es, wn);
+            const float de = es.x, ds = es.y, dw = wn.x, dn = wn.y;
+            const float *__restrict__ p0 = bp + (y0 * pitch + x0);
+            const float *__restrict__ p1 = p0 + pitch;
+            // per tap the weights of (giy, gix) with ATen's signs: nw (-dw, -dn), ne (-de, +dn), sw (+dw, -ds), se (+de, +ds)
+            const float2 c_nw = make_float2(-dw, -dn), c_ne = make_float2(-de, dn), c_sw = make_float2(dw, -ds), c_se = es;
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < CS; ++k) {
+                const float v0 = p0[k * plane], v1 = p0[k * plane + 1], v2 = p1[k * plane], v3 = p1[k * plane + 1];
+                const float2 g2 = x2::bc(gop[k * (kTW * kTH) + r * kTW]);
+                acc = x2::fma(x2::mul(x2::bc(v0), c_nw), g2, acc);
+                acc = x2::fma(x2::mul(x2::bc(v1), c_ne), g2, acc);
+                acc = x2::fma(x2::mul(x2::bc(v2), c_sw), g2, acc);
+                acc = x2::fma(x2::mul(x2::bc(v3), c_se), g2, acc);
+            }
+            acc = x2::mul(gmul2, acc);
+            tma::st_f32_hint(reinterpret_cast<float *>(gq_x), acc.y, pol_first); tma::st_f32_hint(reinterpret_cast<float *>(gq_y), acc.x, pol_first);
+            // (volatile: the unrolled rows otherwise recompute base + r * step with twice the 64-bit adds)
+            asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_x) : "l"(gq_step));
+            asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_y) : "l"(gq_step));
+        }
+    }
+
+    if (kGin) {
+        const unsigned lt = (1u << lane) - 1u;
+        int co = -1, eo = -1;        // linear offsets of the parked south-west / south-east sums' targets; -1: nothing parked
+        float cv[CS], ev[CS];
+#pragma unroll
+        for (int k = 0; k < CS; ++k) { cv[k] = 0.f; ev[k] = 0.f; }
+#pragma unroll 2
+        for (int r = 0; r < kStripRows; ++r) {
+            int x0, y0; float2 es, wn;
+            strip_coords<kAlign, kInter>(mq, r, size2, x0, y0, es, wn);
+            const float de = es.x, ds = es.y, dw = wn.x, dn = wn.y;
+            float go[CS];
+#pragma unroll
+            for (int k = 0; k < CS; ++k) go[k] = gop[k * (kTW * kTH) + r * kTW];
+            const int o = y0 * W + x0;                      // north-west tap; the others are o + 1, o + W, o + W + 1
+            const int o_left = __shfl_up_sync(0xffffffffu, o, 1);
+            // lane l hands its east taps to lane l + 1 when that lane's north-west tap is this lane's north-east one
+            // (x0 <= W - 2 in an interior tile: "offset + 1" never wraps into the next row)
+            const bool take = lane > 0 && o_left + 1 == o;
+            const bool given = ((__ballot_sync(0xffffffffu, take) >> 1) >> lane) & 1u;
+            const bool chain = co == o;                               // the parked south-west sum lands on this row's north-west tap
+            const bool vdup = kVdup && co == o + W;                   // ... on its south-west tap: same source row again
+            const bool broke = co >= 0 && !chain && !vdup;
+            const bool e_chain = kEcarry && eo == o + 1, e_vdup = kEcarry && kVdup && eo == o + W + 1;
+            const bool e_broke = kEcarry && eo >= 0 && !e_chain && !e_vdup;
+            // (scalar: pairs would need as many register moves here as they save multiplies)
+            const float nw = fmul(dw, dn), ne = fmul(de, dn), sw = fmul(dw, ds), se = fmul(de, ds);
+            float et[CS], eb[CS], old_c[CS], old_e[CS];
+#pragma unroll
+            for (int k = 0; k < CS; ++k) {
+                float top = fmul(nw, go[k]), bot = fmul(sw, go[k]);   // west column
+                et[k] = fmul(ne, go[k]); eb[k] = fmul(se, go[k]);     // east column
+                old_e[k] = ev[k];
+                if (e_chain) et[k] += ev[k];                // parked south-east sum: this row's north-east tap
+                if (e_vdup) eb[k] += ev[k];
+                const float pt = __shfl_up_sync(0xffffffffu, et[k], 1), pb = __shfl_up_sync(0xffffffffu, eb[k], 1);
+                if (take) { top += pt; bot += pb; }
+                old_c[k] = cv[k];
+                if (chain) top += cv[k];
+                if (vdup) bot += cv[k];
+                PWS_RED(at(gp[k], o), top);
+                cv[k] = bot;
+                ev[k] = eb[k];
+            }
+            // stragglers -> queue: the east taps nobody took, parked sums whose chain broke
+            if (kEcarry) queue_push<CS>(q, !given, o + 1, et, lt, gp, lane);
+            else queue_push2<CS>(q, !given, o + 1, et, o + W + 1, eb, lt, gp, lane);
+            queue_push<CS>(q, broke, co, old_c, lt, gp, lane);
+            if (kEcarry) queue_push<CS>(q, e_broke, eo, old_e, lt, gp, lane);
+            co = o + W;
+            eo = (kEcarry && !given) ? o + W + 1 : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < CS; ++k) PWS_RED(at(gp[k], co), cv[k]);   // every lane parked a south-west sum in the last row
+        if (kEcarry) queue_push<CS>(q, eo >= 0, eo, ev, lt, gp, lane);
+    }
+}
+
+// The same strip with grad_grid and the scatter of a row fused in one body (one pass over the map and grad_output in shared
+// memory; fewer instructions than the two-phase form, longer dependent chains).
+template <int CS, bool kAlign, bool kInter, bool kGin, bool kGgrid, int SHAPE>
+__device__ __forceinline__ void interior_strip_fused(
+    const int lane, const float *__restrict__ mq /* this lane's map element(s) in the strip's first row */,
+    const float *__restrict__ gop, const float *__restrict__ bp, const int pitch_rt, const int plane_rt,
+    const float2 size2 /* (W, H) as floats; (W-1, H-1) when kAlign */, const int W, const float2 gmul2 /* (gym, gxm) */,
+    float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Queue<CS> &q, const uint64_t pol_first)
+{
+    // SHAPE >= 0: the box's row pitch and plane size are compile-time (one copy of the body per shape); SHAPE < 0: run-time
+    const int kPitch = SHAPE >= 0 ? box_w(SHAPE < 0 ? 0 : SHAPE) : pitch_rt, kPlane = SHAPE >= 0 ? box_w(SHAPE < 0 ? 0 : SHAPE) * box_h(SHAPE < 0 ? 0 : SHAPE) : plane_rt;
     // The two scatter refinements trade ~16 issue slots per row for a quarter fewer queue entries.  The grad_input-only kernel
     // is bound by the RED path and has issue slots to spare (0.383 -> 0.367 ms / 16 1080p frames); the kernel that also
     // computes grad_grid is issue-bound and loses what the RED path gains (0.469 -> 0.474): it keeps the plain scheme.
@@ -424,10 +560,8 @@ __device__ __forceinline__ void interior_strip(
                 acc = x2::fma(x2::mul(x2::bc(v3), c_se), g2, acc);
             }
             acc = x2::mul(gmul2, acc);
-            tma::st_f32_hint(reinterpret_cast<float *>(gq_x), acc.y, pol_first); tma::st_f32_hint(reinterpret_cast<float *>(gq_y), acc.x, pol_first);
-            // (volatile: the unrolled rows otherwise recompute base + r * step with twice the 64-bit adds)
-            asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_x) : "l"(gq_step));
-            asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_y) : "l"(gq_step));
+            tma::st_f32_hint(ggq, acc.y, pol_first); tma::st_f32_hint(ggq + gg_s3, acc.x, pol_first);
+            ggq += gg_s1;
         }
 
         if (kGin) {
@@ -443,28 +577,30 @@ __device__ __forceinline__ void interior_strip(
             const bool broke = r > 0 && !chain && !vdup;
             const bool e_chain = r > 0 && kEcarry && eo == o + 1, e_vdup = r > 0 && kEcarry && kVdup && eo == o + W + 1;
             const bool e_broke = r > 0 && kEcarry && eo >= 0 && !e_chain && !e_vdup;
-            // (scalar: pairs would need as many register moves here as they save multiplies)
-            const float nw = fmul(dw, dn), ne = fmul(de, dn), sw = fmul(dw, ds), se = fmul(de, ds);
+            const float2 ns = make_float2(dn, ds);
+            const float2 w_w = x2::mul(x2::bc(dw), ns), w_e = x2::mul(x2::bc(de), ns);   // (nw, sw), (ne, se)
             float et[CS], eb[CS], old_c[CS], old_e[CS];
 #pragma unroll
             for (int k = 0; k < CS; ++k) {
-                float top = fmul(nw, go[k]), bot = fmul(sw, go[k]);   // west column
-                et[k] = fmul(ne, go[k]); eb[k] = fmul(se, go[k]);     // east column
+                const float2 g2 = x2::bc(go[k]);
+                float2 tb = x2::mul(w_w, g2);               // (top, bottom) of the west column
+                const float2 e2 = x2::mul(w_e, g2);         // ... of the east column
+                et[k] = e2.x; eb[k] = e2.y;
                 old_e[k] = ev[k];
                 if (e_chain) et[k] += ev[k];                // parked south-east sum: this row's north-east tap
                 if (e_vdup) eb[k] += ev[k];
-                const float pt = __shfl_up_sync(0xffffffffu, et[k], 1), pb = __shfl_up_sync(0xffffffffu, eb[k], 1);
-                if (take) { top += pt; bot += pb; }
+                const float2 pe = make_float2(__shfl_up_sync(0xffffffffu, et[k], 1), __shfl_up_sync(0xffffffffu, eb[k], 1));
+                if (take) tb = x2::add(tb, pe);
                 old_c[k] = cv[k];
-                if (chain) top += cv[k];
-                if (vdup) bot += cv[k];
-                PWS_RED(at(gp[k], o), top);
-                cv[k] = bot;
+                if (chain) tb.x += cv[k];
+                if (vdup) tb.y += cv[k];
+                PWS_RED(at(gp[k], o), tb.x);
+                cv[k] = tb.y;
                 ev[k] = eb[k];
             }
             // stragglers -> queue: the north-east tap nobody took, parked sums whose chain broke
-            if (kEcarry) queue_push<CS>(q, !given, o + 1, et, lt, gp, lane);
-            else queue_push2<CS>(q, !given, o + 1, et, o + W + 1, eb, lt, gp, lane);
+            queue_push<CS>(q, !given, o + 1, et, lt, gp, lane);
+            if (!kEcarry) queue_push<CS>(q, !given, o + W + 1, eb, lt, gp, lane);
             queue_push<CS>(q, broke, co, old_c, lt, gp, lane);
             if (kEcarry) queue_push<CS>(q, e_broke, eo, old_e, lt, gp, lane);
             co = o + W;
@@ -547,7 +683,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
         };
         TileCoord tc = tile_coord(min(t, total_tiles - 1), tiles_x, tiles_xy);
         if (lane == 0 && t < total_tiles) load_map(warp, tc);  // the ring starts out empty
-        int zero_seen = -1;  // bands [0, zero_seen] (index = 8 * frame + band) are known to be zero-filled by every CTA
+        int zero_seen = -1;  // bands [0, zero_seen] (index = bands * frame + band) are known to be zero-filled by every CTA
         for (int it = warp;; it += kScouts) {
             const int st = it % kStages, ph = (it / kStages) & 1;
             const int ms = it % kMapStages, mph = (it / kMapStages) & 1;
@@ -582,6 +718,15 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             const int progress = kBands * tc.n + (kBands * (t - tc.n * tiles_xy)) / tiles_xy;  // in bands
             const bool want_box = kGgrid && !(info.z & (kInfoFallback | kInfoEmpty));
             const int shape = info.z & 0xff;
+#if PWS_BWD_L2PF
+            // The tile's operands are known now, its ring stage usually is not free yet: pull grad_output and the frame box
+            // into L2 while the scout waits, so that the real loads below -- issued the moment the stage frees up, one tile
+            // time before the consumers need them -- find them there instead of paying a DRAM round trip under load.
+            if (lane == 0 && !tma::mbar_test(empty + st, ph ^ 1)) {
+                tma::prefetch_l2_4d(&tp.gout, tc.w0, tc.h0, 0, n_begin + tc.n);
+                if (want_box) tma::prefetch_l2_4d(&tp.box[shape], info.x, info.y, 0, n_begin + tc.n);
+            }
+#endif
             tma::mbar_wait_relaxed(empty + st, ph ^ 1);
             if (lane == 0) {
                 s_info[2 * st] = info;
@@ -596,10 +741,10 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                     // the zero-fill warp keeps `zero_ahead` bands ahead of what the scouts publish: the output position of
                     // the tile, or the band it needs if that is further on (a map that samples far away must not starve)
                     progress_store(&s_progress[warp], max(progress, need));
-                    if (need > zero_seen) {  // bands complete in order: every CTA fills them in order
-                        while (ld_acquire(&g_zero_done[slot][need]) < gridDim.x) __nanosleep(64);
-                        zero_seen = need;
-                    }
+                    // (the zero-fill warps of a CTA take the bands round-robin: completion is not in order, check every band)
+                    for (int b = zero_seen + 1; b <= need; ++b)
+                        while (ld_acquire(&g_zero_done[slot][b]) < gridDim.x) __nanosleep(64);
+                    zero_seen = max(zero_seen, need);
                 } else if (kGin) {
                     progress_store(&s_progress[warp], progress);
                 }
@@ -613,14 +758,15 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             t = t1; tc = tc1;
             t1 = __shfl_sync(0xffffffffu, t2, 0);
         }
-    } else if (warp == kZeroWarp) {
-        // ===== zero-fill of grad_input, band by band, this CTA's 1/gridDim share of every band, `zero_ahead` bands ahead =====
+    } else if (warp >= kZeroWarp) {
+        // ===== zero-fill of grad_input: this CTA's 1/gridDim share of every band, kZeroAhead bands ahead of the scouts; the
+        // zero-fill warps take the bands round-robin =====
         if (kGin) {
             const int64_t plane = (int64_t)g.H * g.W;  // dense NCHW frame (host-checked), W % 4 == 0, base 16-byte aligned
             const int last = n_frames * kBands - 1;
-            for (int idx = 0; idx <= last; ++idx) {
+            for (int idx = warp - kZeroWarp; idx <= last; idx += kZeroWarps) {
                 const int f = idx / kBands, b = idx % kBands;
-                while (max(progress_load(&s_progress[0]), progress_load(&s_progress[1])) + kZeroAhead < idx) __nanosleep(256);
+                while (max(progress_load(&s_progress[0]), progress_load(&s_progress[1])) + kZeroAhead < idx) __nanosleep(PWS_BWD_ZERO_POLL_NS);
                 const int r0 = (b * g.H + kBands - 1) / kBands, r1 = ((b + 1) * g.H + kBands - 1) / kBands;
                 const int band_vec = (r1 - r0) * (g.W / 4);  // float4 per channel plane
                 const int share = (band_vec + gridDim.x - 1) / gridDim.x;
@@ -630,9 +776,16 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                     float4 *__restrict__ dst = reinterpret_cast<float4 *>(fp + c * plane);
                     for (int v = v0 + lane; v < v1; v += 32) tma::st_zero_v4_hint(dst + v, pol_zero);
                 }
+#ifdef PWS_BWD_RELEASE_RED
+                // the warp's stores are ordered before lane 0's release by the warp barrier; the release makes them visible
+                // at gpu scope together with the count
+                __syncwarp();
+                if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&g_zero_done[slot][idx]) : "memory");
+#else
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(&g_zero_done[slot][idx], 1u);
+#endif
             }
         }
     } else {
@@ -671,20 +824,20 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
 
             if (info.z & kInfoInterior) {
                 // the box address of source pixel (x, y) is bp + y * pitch + x: fold the box origin into the base
+                const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
+#if PWS_BWD_STRIP == 0
+                interior_strip<CS, kAlign, kInter, kGin, kGgrid>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane,
+                                                                 size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
+#elif PWS_BWD_STRIP == 1
+                interior_strip_fused<CS, kAlign, kInter, kGin, kGgrid, -1>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane,
+                                                                           size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
+#else
                 switch (shape) {
-                case 0:
-                    interior_strip<CS, kAlign, kInter, kGin, kGgrid, 0>(lane, mp + map_lane, gop, box0 - (info.y * box_w(0) + info.x), size2, g.W, gmul2,
-                                                                       gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
-                    break;
-                case 1:
-                    interior_strip<CS, kAlign, kInter, kGin, kGgrid, 1>(lane, mp + map_lane, gop, box0 - (info.y * box_w(1) + info.x), size2, g.W, gmul2,
-                                                                       gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
-                    break;
-                default:
-                    interior_strip<CS, kAlign, kInter, kGin, kGgrid, 2>(lane, mp + map_lane, gop, box0 - (info.y * box_w(2) + info.x), size2, g.W, gmul2,
-                                                                       gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
-                    break;
+                case 0: interior_strip_fused<CS, kAlign, kInter, kGin, kGgrid, 0>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane, size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg); break;
+                case 1: interior_strip_fused<CS, kAlign, kInter, kGin, kGgrid, 1>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane, size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg); break;
+                default: interior_strip_fused<CS, kAlign, kInter, kGin, kGgrid, 2>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane, size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg); break;
                 }
+#endif
             } else {
                 const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
                 const float *__restrict__ ip = (const float *)in.p + (int64_t)n * in.sN;
@@ -723,7 +876,10 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
     if (!lease.ok()) return false;  // stream capture: the caller takes the memset + non-persistent kernel path
     int slot = lease.slot();
     const int64_t frame_bytes = (int64_t)CS * pb.g.H * pb.g.W * 4;
-    int bands = (int)((frame_bytes + (2 << 20) - 1) / (2 << 20));
+#ifndef PWS_BWD_BAND_MB
+#define PWS_BWD_BAND_MB 4
+#endif
+    int bands = (int)((frame_bytes + ((int64_t)PWS_BWD_BAND_MB << 20) - 1) / ((int64_t)PWS_BWD_BAND_MB << 20));
     bands = bands < 1 ? 1 : bands > kMaxBands ? kMaxBands : bands;
     // The scouts wait for EVERY CTA of the launch to have zero-filled a band of grad_input: all CTAs must be resident at
     // the same time.  A cooperative launch makes the driver guarantee that (or refuse the launch: SM-limited contexts

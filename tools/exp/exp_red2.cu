@@ -28,6 +28,14 @@ __global__ void k(float *p, unsigned n_lines, int reps)
         if (MODE == 5) red(p + (size_t)(hash(h + (lane >> 2) * 7919u) % n_lines) * 32 + (lane & 3) * 8, 1.f);
         if (MODE == 6) { if (lane < 3) red(p + (size_t)(hash(h + lane * 7919u) % n_lines) * 32 + lane, 1.f); }
         if (MODE == 7) red(base + (size_t)(hash(h + lane) % 60) * 32 + lane, 1.f);
+        // patterns of the marching scatter's "tops": a 32-pixel output row on a stretched, slanted map
+        if (MODE == 8) red(base + 5 + lane - (lane > 13), 1.f);                       // consecutive, one duplicate address
+        if (MODE == 9) red(base + 5 + lane + (lane > 13), 1.f);                       // consecutive, one gap
+        if (MODE == 10) red(base + 5 + lane + (lane > 17 ? 1920 : 0), 1.f);           // slanted: the row continues one frame row (1920 floats) down
+        if (MODE == 11) red(base + 5 + lane + (lane > 9 ? 1920 : 0) + (lane > 21 ? 1921 : 0) - (lane > 15), 1.f);   // two slants, a dup
+        if (MODE == 12) { if (lane < 16) red(base + 5 + lane, 1.f); }                 // half a warp, consecutive
+        if (MODE == 13) { red(base + 5 + lane, 1.f); red(base + 1920 + 5 + lane, 1.f); }   // two consecutive REDs, adjacent frame rows
+        if (MODE == 14) { if (lane <= 17) red(base + 5 + lane, 1.f); if (lane > 17) red(base + 1920 + 5 + lane, 1.f); }   // the slanted row as two predicated consecutive REDs
     }
 }
 
@@ -65,6 +73,13 @@ int main()
         run<5>("32 lanes, 8 random lines, 4 sectors each (32 sectors)", 32, p, n);
         run<4>("8 lanes, 8 random lines (8 sectors)", 8, p, n);
         run<6>("3 lanes, 3 random lines (3 sectors)", 3, p, n);
+        run<8>("consecutive with one duplicate address", 4, p, n);
+        run<9>("consecutive with one gap", 5, p, n);
+        run<10>("slanted row: 18 + 14 lanes, 1920 floats apart", 6, p, n);
+        run<11>("two slants and a duplicate", 8, p, n);
+        run<12>("16 of 32 lanes, consecutive", 3, p, n);
+        run<13>("two full consecutive REDs (per pair)", 10, p, n);
+        run<14>("slanted row as two predicated consecutive REDs (per pair)", 6, p, n);
     }
     return 0;
 }
