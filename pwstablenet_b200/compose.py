@@ -113,6 +113,11 @@ def warp_fused(frame: torch.Tensor, drift: Optional[torch.Tensor] = None, base: 
             raise RuntimeError("warp_fused: map_size is required when there is no drift")
         drift = compose_map(n, map_size, drift, base, theta, base_align_corners, None, map_size, device=frame.device)
         base, theta = "none", None
+    if upsample is not None and drift is not None and base == "none" and not drift.is_contiguous():
+        # netG hands its map over as a permuted view of planar storage (R/lib/networks_cascading.py:235-237); the
+        # specialised inference kernel reads an interleaved lattice with 8-byte loads.  Repacking 0.5 MB per frame is
+        # nothing next to the frame; the values, hence the result, are the same.
+        drift = drift.contiguous()
     spec = _spec(n, drift, base, theta, base_align_corners, upsample, map_size, pre, post, keep)
     if out_size is None:
         out_size = (spec.map_h, spec.map_w)

@@ -64,3 +64,37 @@ def tile_basis(t: int, device=None) -> torch.Tensor:
     q12 = (x2 - x) * y / (x2 * y2)
     q22 = x * y / (x2 * y2)
     return torch.stack([q11, q21, q12, q22], dim=-1).reshape(t * t, 4)
+
+
+def crop_resize_batch(sequence: torch.Tensor, affine: torch.Tensor, sampler=None) -> torch.Tensor:
+    """`frame_clip_batchsize` (R/lib/utils.py:304-336, the GAN branch's crop helper) as ONE warp call with no host round trip.
+
+    The reference maps the four frame corners through every sample's affine, intersects the boxes over the batch
+    (`.cpu().numpy()` synchronisations), slices that box out of every sample in a Python loop, resizes each slice to the
+    frame size with `nn.Upsample(mode='bilinear')` and writes the results into a CPU tensor.  A crop followed by a
+    half-pixel bilinear resize IS a bilinear sample on an axis-aligned lattice: here the box stays on the device, the
+    lattice `src = (j + 0.5) * crop / size - 0.5 + origin` (clamped to the crop, as the resize clamps at its borders) is
+    built with a few elementwise ops and the whole batch is one `grid_sample` call (padding 'border', align_corners=False) --
+    through `torch.nn.functional.grid_sample`, i.e. this library's kernel once `install()` has run.
+
+    sequence (N,C,S,S); affine (N,6) or (N,2,3).  Returns (N,C,S,S) on sequence's device."""
+    import torch.nn.functional as F
+    sampler = sampler or F.grid_sample
+    n, c, s, s2 = sequence.shape
+    assert s == s2, "the reference crops square frames (opt.input_size)"
+    dev, dt = sequence.device, sequence.dtype
+    boundary = torch.tensor([[-1, -1, 1], [1, -1, 1], [-1, 1, 1], [1, 1, 1]], dtype=dt, device=dev).t()      # (3,4)
+    bound = torch.matmul(affine.view(-1, 2, 3).to(dt), boundary)                                           # (N,2,4)
+    x_s = bound[:, 0, [0, 2]].max().clamp_min(-1.0); x_e = bound[:, 0, [1, 3]].min().clamp_max(1.0)
+    y_s = bound[:, 1, [0, 1]].max().clamp_min(-1.0); y_e = bound[:, 1, [2, 3]].min().clamp_max(1.0)
+    # int(...) truncates; the bounds are >= 0 here
+    x0 = ((x_s + 1) * s / 2).trunc(); x1 = ((x_e + 1) * s / 2).trunc()
+    y0 = ((y_s + 1) * s / 2).trunc(); y1 = ((y_e + 1) * s / 2).trunc()
+    j = torch.arange(s, dtype=dt, device=dev) + 0.5
+    sx = (j * ((x1 - x0) / s) - 0.5).clamp_min(0.0) + x0           # upsample_bilinear2d's source index, in frame pixels
+    sy = (j * ((y1 - y0) / s) - 0.5).clamp_min(0.0) + y0
+    sx = torch.minimum(sx, x1 - 1); sy = torch.minimum(sy, y1 - 1)  # the +1 neighbour stays inside the crop
+    gx = (2 * sx + 1) / s - 1                                       # normalised, align_corners=False
+    gy = (2 * sy + 1) / s - 1
+    grid = torch.stack([gx.view(1, s).expand(s, s), gy.view(s, 1).expand(s, s)], dim=-1).unsqueeze(0).expand(n, s, s, 2)
+    return sampler(sequence, grid.contiguous(), mode="bilinear", padding_mode="border", align_corners=False)

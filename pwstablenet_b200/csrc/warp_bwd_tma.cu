@@ -59,6 +59,9 @@ constexpr int kScouts = 2, kGroups = 2, kGroupWarps = 8, kConsumers = kGroups * 
 #ifndef PWS_BWD_ZERO_POLL_NS
 #define PWS_BWD_ZERO_POLL_NS 1000
 #endif
+#ifndef PWS_BWD_STATIC_TILES
+#define PWS_BWD_STATIC_TILES 0
+#endif
 #ifndef PWS_BWD_L2PF
 #define PWS_BWD_L2PF 0   // measured: 0.434 -> 0.442 ms with it (the loads are not what the consumers wait for)
 #endif
@@ -698,7 +701,11 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 break;
             }
             int t2 = 0;
+#if PWS_BWD_STATIC_TILES   // experiment: static round-robin instead of the launch's counter
+            t2 = t1 + stride;
+#else
             if (lane == 0) t2 = (int)atomicAdd(&g_tile_next[slot], 1u) + 2 * stride;  // the tile after the next
+#endif
             const TileCoord tc1 = tile_coord(min(t1, total_tiles - 1), tiles_x, tiles_xy);
             // next tile's map: its slot was last used kMapStages iterations ago and is normally free by now
             bool next_loaded = t1 >= total_tiles;

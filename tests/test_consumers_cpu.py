@@ -93,3 +93,33 @@ def test_block_affine_residual_equals_the_concatenated_least_squares():
     ref = torch.dist(ab, bt, 1).to(torch.float32)
     got = C.block_affine_residual(drift, basis, blocks)
     assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
+
+
+def restated_frame_clip_batchsize(sequence, affine, size):
+    # R/lib/utils.py:304-336 on the CPU (the reference's own function hard-codes .cuda() and opt.batchSize)
+    n = sequence.size(0)
+    boundary = torch.tensor([[-1, -1, 1], [1, -1, 1], [-1, 1, 1], [1, 1, 1]], dtype=torch.float32).expand(n, 4, 3).permute(0, 2, 1)
+    bound = torch.matmul(affine.view(-1, 2, 3), boundary)
+    x_start = bound[:, 0, [0, 2]].numpy(); x_end = bound[:, 0, [1, 3]].numpy()
+    y_start = bound[:, 1, [0, 1]].numpy(); y_end = bound[:, 1, [2, 3]].numpy()
+    xs, xe, ys, ye = -1, 1, -1, 1
+    for i in range(n):
+        xs = max(xs, max(max(x_start[i]), -1)); xe = min(xe, min(min(x_end[i]), 1))
+        ys = max(ys, max(max(y_start[i]), -1)); ye = min(ye, min(min(y_end[i]), 1))
+    out = torch.empty_like(sequence)
+    m = torch.nn.Upsample(size=size, mode="bilinear")
+    for i in range(n):
+        out[i] = m(sequence[i:i + 1, :, int((ys + 1) * size / 2):int((ye + 1) * size / 2), int((xs + 1) * size / 2):int((xe + 1) * size / 2)])[0]
+    return out
+
+
+def test_crop_resize_equals_slice_plus_upsample():
+    g = torch.Generator().manual_seed(5)
+    n, size = 4, 64
+    seq = torch.rand((n, 3, size, size), generator=g)
+    affine = torch.tensor([1.0, 0, 0, 0, 1, 0]).repeat(n, 1) + torch.randn((n, 6), generator=g) * 0.05
+    affine[:, 0] = 0.8 + 0.05 * torch.rand(n, generator=g)      # shrink: the warped frame leaves a border to crop away
+    affine[:, 4] = 0.85 + 0.05 * torch.rand(n, generator=g)
+    ref = restated_frame_clip_batchsize(seq, affine, size)
+    got = C.crop_resize_batch(seq, affine)
+    assert float((got - ref).abs().max()) <= 2e-6

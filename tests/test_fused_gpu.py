@@ -169,6 +169,8 @@ def test_inference_site_is_byte_exact_against_the_torch_cuda_pipeline(pw):
         want = fake[0].permute(1, 2, 0).cpu().numpy().astype(np.uint8)
         out = pw.warp_fused(hwc.permute(0, 3, 1, 2), drift=lattice.permute(0, 2, 3, 1), upsample="aligned", out_size=(H, W),
                             out_dtype=torch.uint8, out_channels_last=True)
+        from pwstablenet_b200 import _lib
+        assert _lib.last_kernel() == "fwd_fused_u8"       # netG's planar map view is repacked for the specialised kernel
         got = out[0].permute(1, 2, 0).contiguous().cpu().numpy()
         assert np.array_equal(got, want), (H, W, int((got != want).sum()))
 

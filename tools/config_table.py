@@ -123,3 +123,18 @@ aten_ms = t(lambda: fb(lambda: [torch.ops.aten.grid_sampler_2d((fr + 1) * 127.5,
 row("config 3: the same, forward + backward through autograd (grad to the three maps)", ms, (3 * 4 + 3 * (8 + 12) + 3 * 4 + 3 * (12 + 8 + 8)) * N * H * W, N, k, aten_ms)
 ours_ms = t(lambda: fb(lambda: [pw.grid_sample((fr + 1) * 127.5, g, "bilinear", "zeros", False) / 127.5 - 1 for g in gr3]), 30)
 print(f"| (the same through three pw.grid_sample calls + torch elementwise ops: {ours_ms:.3f} ms) | | | | | | |")
+
+# sensitivity of the backward to the roughness of the map (the bench map stretches by up to +-12 %)
+N, C, H, W = 16, 3, 1080, 1920
+fr = torch.rand(N, C, H, W, device="cuda") * 255
+go = torch.rand(N, C, H, W, device="cuda")
+rng = np.random.default_rng(1)
+ident = synth.identity_map(4, H, W, False)
+for name, gmap in (("identity map", ident),
+                   ("identity + 0.03 tanh(noise on a 3x3 lattice): stretch <= 3 %", ident + synth.smooth_drift(4, H, W, rng, amp=0.03, ncell=2)),
+                   ("bench map (9x9 lattice): stretch <= 12 %", synth.make_map("smooth", 4, H, W, False, seed=1))):
+    g = planar(torch.from_numpy(np.ascontiguousarray(gmap, dtype=np.float32)).cuda().repeat(4, 1, 1, 1).contiguous())
+    ms = t(lambda: pw.warp2d_backward(go, fr, g, 0, False, (True, True)), 20); k = _lib.last_kernel()
+    row(f"1080p backward (both gradients), {name}", ms, 52 * N * H * W, N, k)
+    ms = t(lambda: pw.warp2d_backward(go, fr, g, 0, False, (True, False)), 20)
+    row(f"1080p backward, grad to frame only, {name}", ms, 32 * N * H * W, N, k)

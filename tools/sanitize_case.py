@@ -6,6 +6,7 @@ import torch
 import pwstablenet_b200 as pw
 from pwstablenet_b200 import _lib
 import synth
+_lib.small_problem_elems(0)      # reach the persistent TMA kernels with this small case
 N, C, H, W = 3, 3, 144, 256
 for kind in ("smooth", "noisy"):
     g = torch.from_numpy(synth.make_map(kind, N, H, W, False, seed=1)).cuda()
@@ -23,4 +24,12 @@ for kind in ("smooth", "noisy"):
         torch.cuda.synchronize()
         ref = torch.ops.aten.grid_sampler_2d(fr, grid, 0, 0, False)
         print(kind, k1, k2, k3, k4, bool(torch.equal(out, ref)), float(gi.sum()), flush=True)
+# the multi-map op and the 16-bit backward
+fr = torch.rand(N, C, H, W, device="cuda") * 2 - 1
+gs = [torch.from_numpy(synth.make_map("smooth", N, H, W, False, seed=s)).cuda().requires_grad_(True) for s in (1, 2, 3)]
+outs = pw.warp_stages(fr, gs, pre=(1.0, 127.5), post=(127.5, -1.0))
+torch.autograd.backward(list(outs), [torch.ones_like(o) for o in outs])
+gi16, gg16 = pw.warp2d_backward(go.bfloat16(), (fr * 100).bfloat16(), gp, 0, False, (True, True))
+torch.cuda.synchronize()
+print("stages + 16-bit backward", float(gs[0].grad.abs().sum()), float(gi16.float().abs().sum()), flush=True)
 print("sanitize case done")
