@@ -136,7 +136,7 @@ template <int CS, bool kGgrid> struct Smem {
     static constexpr int kQueueOff = kBoxOff + kStages * kBoxBytes;
     static constexpr int kQueueEntry = CS == 3 ? 16 : 8;
     static constexpr int kInfoOff = kQueueOff + kConsumers * kQueueCap * kQueueEntry;
-    static constexpr int kBarOff = kInfoOff + kStages * 32;
+    static constexpr int kBarOff = kInfoOff + kStages * 48;   // per stage: info, where, two base pointers
     static constexpr int kProgressOff = kBarOff + 2 * (kStages + kMapStages) * 8;
     static constexpr int kTotal = kProgressOff + 16;
     static_assert(kGoutBytes % 128 == 0 && kBoxBytes % 128 == 0, "TMA destinations must stay 128-byte aligned");
@@ -511,7 +511,7 @@ __device__ __forceinline__ void interior_strip(
 }
 
 // The same strip with grad_grid and the scatter of a row fused in one body (one pass over the map and grad_output in shared
-// memory; fewer instructions than the two-phase form, longer dependent chains).
+// memory; fewer instructions than the two-phase form, longer dependent chains).  The product form.
 template <int CS, bool kAlign, bool kInter, bool kGin, bool kGgrid, int SHAPE>
 __device__ __forceinline__ void interior_strip_fused(
     const int lane, const float *__restrict__ mq /* this lane's map element(s) in the strip's first row */,
@@ -521,6 +521,9 @@ __device__ __forceinline__ void interior_strip_fused(
 {
     // SHAPE >= 0: the box's row pitch and plane size are compile-time (one copy of the body per shape); SHAPE < 0: run-time
     const int kPitch = SHAPE >= 0 ? box_w(SHAPE < 0 ? 0 : SHAPE) : pitch_rt, kPlane = SHAPE >= 0 ? box_w(SHAPE < 0 ? 0 : SHAPE) * box_h(SHAPE < 0 ? 0 : SHAPE) : plane_rt;
+    // the two grad_grid stores of a pixel: running byte pointers, one 64-bit add each per row
+    char *gq_x = reinterpret_cast<char *>(ggq), *gq_y = reinterpret_cast<char *>(ggq + gg_s3);
+    const int64_t gq_step = (int64_t)gg_s1 * 4;
     // The two scatter refinements trade ~16 issue slots per row for a quarter fewer queue entries.  The grad_input-only kernel
     // is bound by the RED path and has issue slots to spare (0.383 -> 0.367 ms / 16 1080p frames); the kernel that also
     // computes grad_grid is issue-bound and loses what the RED path gains (0.469 -> 0.474): it keeps the plain scheme.
@@ -563,8 +566,10 @@ __device__ __forceinline__ void interior_strip_fused(
                 acc = x2::fma(x2::mul(x2::bc(v3), c_se), g2, acc);
             }
             acc = x2::mul(gmul2, acc);
-            tma::st_f32_hint(ggq, acc.y, pol_first); tma::st_f32_hint(ggq + gg_s3, acc.x, pol_first);
-            ggq += gg_s1;
+            tma::st_f32_hint(reinterpret_cast<float *>(gq_x), acc.y, pol_first); tma::st_f32_hint(reinterpret_cast<float *>(gq_y), acc.x, pol_first);
+            // (volatile: the unrolled rows otherwise recompute base + r * step with twice the 64-bit adds)
+            asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_x) : "l"(gq_step));
+            asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_y) : "l"(gq_step));
         }
 
         if (kGin) {
@@ -580,30 +585,28 @@ __device__ __forceinline__ void interior_strip_fused(
             const bool broke = r > 0 && !chain && !vdup;
             const bool e_chain = r > 0 && kEcarry && eo == o + 1, e_vdup = r > 0 && kEcarry && kVdup && eo == o + W + 1;
             const bool e_broke = r > 0 && kEcarry && eo >= 0 && !e_chain && !e_vdup;
-            const float2 ns = make_float2(dn, ds);
-            const float2 w_w = x2::mul(x2::bc(dw), ns), w_e = x2::mul(x2::bc(de), ns);   // (nw, sw), (ne, se)
+            // (scalar: pairs would need as many register moves here as they save multiplies)
+            const float nw = fmul(dw, dn), ne = fmul(de, dn), sw = fmul(dw, ds), se = fmul(de, ds);
             float et[CS], eb[CS], old_c[CS], old_e[CS];
 #pragma unroll
             for (int k = 0; k < CS; ++k) {
-                const float2 g2 = x2::bc(go[k]);
-                float2 tb = x2::mul(w_w, g2);               // (top, bottom) of the west column
-                const float2 e2 = x2::mul(w_e, g2);         // ... of the east column
-                et[k] = e2.x; eb[k] = e2.y;
+                float top = fmul(nw, go[k]), bot = fmul(sw, go[k]);   // west column
+                et[k] = fmul(ne, go[k]); eb[k] = fmul(se, go[k]);     // east column
                 old_e[k] = ev[k];
                 if (e_chain) et[k] += ev[k];                // parked south-east sum: this row's north-east tap
                 if (e_vdup) eb[k] += ev[k];
-                const float2 pe = make_float2(__shfl_up_sync(0xffffffffu, et[k], 1), __shfl_up_sync(0xffffffffu, eb[k], 1));
-                if (take) tb = x2::add(tb, pe);
+                const float pt = __shfl_up_sync(0xffffffffu, et[k], 1), pb = __shfl_up_sync(0xffffffffu, eb[k], 1);
+                if (take) { top += pt; bot += pb; }
                 old_c[k] = cv[k];
-                if (chain) tb.x += cv[k];
-                if (vdup) tb.y += cv[k];
-                PWS_RED(at(gp[k], o), tb.x);
-                cv[k] = tb.y;
+                if (chain) top += cv[k];
+                if (vdup) bot += cv[k];
+                PWS_RED(at(gp[k], o), top);
+                cv[k] = bot;
                 ev[k] = eb[k];
             }
             // stragglers -> queue: the north-east tap nobody took, parked sums whose chain broke
-            queue_push<CS>(q, !given, o + 1, et, lt, gp, lane);
-            if (!kEcarry) queue_push<CS>(q, !given, o + W + 1, eb, lt, gp, lane);
+            if (kEcarry) queue_push<CS>(q, !given, o + 1, et, lt, gp, lane);
+            else queue_push2<CS>(q, !given, o + 1, et, o + W + 1, eb, lt, gp, lane);
             queue_push<CS>(q, broke, co, old_c, lt, gp, lane);
             if (kEcarry) queue_push<CS>(q, e_broke, eo, old_e, lt, gp, lane);
             co = o + W;
@@ -694,7 +697,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             if (t >= total_tiles) {
                 tma::mbar_wait_relaxed(empty + st, ph ^ 1);
                 if (lane == 0) {
-                    s_info[2 * st] = make_int4(0, 0, kInfoStop, 0);
+                    s_info[3 * st] = make_int4(0, 0, kInfoStop, 0);
                     tma::mbar_arrive(full + st); tma::mbar_arrive(full + st);
                     progress_store(&s_progress[warp], INT_MAX - kZeroAhead);  // out of tiles: let the zero-fill warp run to the end
                 }
@@ -736,8 +739,16 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
 #endif
             tma::mbar_wait_relaxed(empty + st, ph ^ 1);
             if (lane == 0) {
-                s_info[2 * st] = info;
-                s_info[2 * st + 1] = make_int4(tc.h0, tc.w0, 0, 0);
+                s_info[3 * st] = info;
+                s_info[3 * st + 1] = make_int4(tc.h0, tc.w0, 0, 0);
+                // the tile's base pointers, computed once here instead of by each of the group's eight warps: this frame's
+                // grad_input plane 0 and the tile's first grad_grid element
+                {
+                    const uint64_t p_gin = kGin ? reinterpret_cast<uint64_t>((float *)gin.p + (int64_t)(n_begin + tc.n) * gin.sN) : 0;
+                    const uint64_t p_gg = kGgrid ? reinterpret_cast<uint64_t>((float *)ggrid.p + ((int64_t)(n_begin + tc.n) * ggrid.sN +
+                                                                                               (int64_t)tc.h0 * ggrid.s1 + (int64_t)tc.w0 * ggrid.s2)) : 0;
+                    reinterpret_cast<ulonglong2 *>(s_info)[3 * st + 2] = make_ulonglong2(p_gin, p_gg);
+                }
                 tma::mbar_arrive_expect_tx(full + st, S::kGoutBytes + (want_box ? box_w(shape) * box_h(shape) * CS * 4 : 0));
                 tma::load_4d_hint(s_gout + (size_t)st * S::kGoutBytes, &tp.gout, full + st, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
                 if (want_box) tma::load_4d_hint(s_box + (size_t)st * S::kBoxBytes, &tp.box[shape], full + st, info.x, info.y, 0, n_begin + tc.n, pol_box);
@@ -814,7 +825,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             // one warp of the group waits on the stage's mbarrier, the others park on a hardware barrier and spin on nothing
             if (wg == 0) tma::mbar_wait(full + is, ph);
             tma::named_bar_sync(1 + grp, kGroupWarps * 32);
-            const int4 info = s_info[2 * is], where = s_info[2 * is + 1];
+            const int4 info = s_info[3 * is], where = s_info[3 * is + 1];
             if (info.z & kInfoStop) break;
             const int n = n_begin + info.w;
             const int shape = info.z & 0xff;
@@ -823,11 +834,12 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             const float *gop = reinterpret_cast<const float *>(s_gout + (size_t)is * S::kGoutBytes) + gout_lane;
             const float *box0 = reinterpret_cast<const float *>(s_box + (size_t)is * S::kBoxBytes);
             // this frame's grad_input planes: one 64-bit base per channel, source pixels are 32-bit offsets from them
+            const ulonglong2 base = reinterpret_cast<const ulonglong2 *>(s_info)[3 * is + 2];   // published by the scout
             float *gp[CS];
-            gp[0] = kGin ? (float *)gin.p + (int64_t)n * gin.sN : nullptr;
+            gp[0] = reinterpret_cast<float *>(base.x);
 #pragma unroll
             for (int k = 1; k < CS; ++k) gp[k] = gp[k - 1] + plane_elems;
-            float *__restrict__ ggq = kGgrid ? (float *)ggrid.p + ((int64_t)n * ggrid.sN + (int64_t)where.x * ggrid.s1 + (int64_t)where.y * ggrid.s2 + gg_lane) : nullptr;
+            float *__restrict__ ggq = kGgrid ? reinterpret_cast<float *>(base.y) + gg_lane : nullptr;
 
             if (info.z & kInfoInterior) {
                 // the box address of source pixel (x, y) is bp + y * pitch + x: fold the box origin into the base
