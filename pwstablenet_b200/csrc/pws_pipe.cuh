@@ -20,7 +20,15 @@ constexpr int kNumShapes = 3;
 // (Measured and dropped: 96-wide boxes, whose row pitch is a multiple of the 32 banks.  They remove the 2-way bank
 // conflicts between lanes that sample different box rows -- 43 % of the backward's tap reads take a second wavefront --
 // but the extra box bytes and the lower height limit cost more than the conflicts: 0.480 vs 0.467 ms.)
-constexpr int kBW0 = 72, kBH0 = 20, kBW1 = 80, kBH1 = 24, kBW2 = 88, kBH2 = 27;
+#ifndef PWS_BW0   // (overridable for A/B builds: tools/build_variant.py)
+#define PWS_BW0 72
+#define PWS_BH0 20
+#define PWS_BW1 80
+#define PWS_BH1 24
+#define PWS_BW2 88
+#define PWS_BH2 27
+#endif
+constexpr int kBW0 = PWS_BW0, kBH0 = PWS_BH0, kBW1 = PWS_BW1, kBH1 = PWS_BH1, kBW2 = PWS_BW2, kBH2 = PWS_BH2;
 constexpr int kMaxBW = kBW2, kMaxBH = kBH2;
 __host__ __device__ constexpr int box_w(int s) { return s == 0 ? kBW0 : s == 1 ? kBW1 : kBW2; }
 __host__ __device__ constexpr int box_h(int s) { return s == 0 ? kBH0 : s == 1 ? kBH1 : kBH2; }

@@ -32,7 +32,14 @@ namespace {
 
 // explicit fire-and-forget reduction: with a fence elsewhere in the kernel nvcc turns atomicAdd into the
 // returning ATOMG form, whose round trip to L2 the scatter would then wait for
+#ifndef PWS_KO   // development, TIMING ONLY (results are wrong): knock out one path to see what it costs beyond its issue slots
+#define PWS_KO 0 // 1: zero-fill stores, 2: REDs, 4: grad_grid stores, 8: the scouts' wait for zero-filled bands, 16: tap loads,
+#endif           // 32: the scatter's shuffles, 64: the whole interior strip, 128: the straggler queue (tools/map_bench.py)
+#if PWS_KO & 2
+#define PWS_RED(p, v) do { const float v_ = (v); if (__float_as_int(v_) == 0x7fc12345) tma::red_add_f32((p), v_); } while (0)
+#else
 #define PWS_RED(p, v) tma::red_add_f32((p), (v))
+#endif
 
 // Scatter refinements of the interior body (development builds may switch them off to measure their share):
 //   east carry    an east-bottom tap nobody takes over is parked like the south-west sum and merges into the lane's own
@@ -93,7 +100,10 @@ __device__ unsigned int g_exit_count[kSyncSlots];
 __device__ unsigned int g_tile_next[kSyncSlots];
 // (slots are leased per device and reused only after their previous launch has finished: pws_launch.cuh)
 // how far the zero-fill runs ahead of the scatter, in bands
-constexpr int kZeroAhead = 4;
+#ifndef PWS_BWD_ZERO_AHEAD
+#define PWS_BWD_ZERO_AHEAD 4
+#endif
+constexpr int kZeroAhead = PWS_BWD_ZERO_AHEAD;
 
 // the scouts' progress words: a flag polled by the zero-fill warp, not data
 #ifdef PWS_BWD_ATOMIC_PROGRESS   // shared-memory atomics: silences compute-sanitizer's racecheck (used for the sanitizer runs)
@@ -417,9 +427,8 @@ __device__ __forceinline__ void interior_strip(
     const float2 size2 /* (W, H) as floats; (W-1, H-1) when kAlign */, const int W, const float2 gmul2 /* (gym, gxm) */,
     float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Queue<CS> &q, const uint64_t pol_first)
 {
-    // The two scatter refinements trade ~16 issue slots per row for a quarter fewer queue entries.  The grad_input-only kernel
-    // is bound by the RED path (0.383 -> 0.367 ms / 16 1080p frames); the kernel that also computes grad_grid gains nothing.
-    constexpr bool kEcarry = PWS_BWD_ECARRY && !kGgrid, kVdup = PWS_BWD_VDUP && !kGgrid;
+    // The two scatter refinements trade ~16 issue slots per row for a quarter fewer queue entries.
+    constexpr bool kEcarry = PWS_BWD_ECARRY, kVdup = PWS_BWD_VDUP;
 
     if (kGgrid) {
         // the two grad_grid stores of a pixel: running byte pointers, one 64-bit add each per row
@@ -524,10 +533,10 @@ __device__ __forceinline__ void interior_strip_fused(
     // the two grad_grid stores of a pixel: running byte pointers, one 64-bit add each per row
     char *gq_x = reinterpret_cast<char *>(ggq), *gq_y = reinterpret_cast<char *>(ggq + gg_s3);
     const int64_t gq_step = (int64_t)gg_s1 * 4;
-    // The two scatter refinements trade ~16 issue slots per row for a quarter fewer queue entries.  The grad_input-only kernel
-    // is bound by the RED path and has issue slots to spare (0.383 -> 0.367 ms / 16 1080p frames); the kernel that also
-    // computes grad_grid is issue-bound and loses what the RED path gains (0.469 -> 0.474): it keeps the plain scheme.
-    constexpr bool kEcarry = PWS_BWD_ECARRY && !kGgrid, kVdup = PWS_BWD_VDUP && !kGgrid;
+    // The two scatter refinements trade ~16 issue slots per row for a quarter fewer queue entries: 0.383 -> 0.367 ms / 16
+    // 1080p frames in the grad_input-only kernel, 0.426 -> 0.409 in the kernel that also computes grad_grid.  (While a single
+    // zero-fill warp still paced that kernel the same switch measured as a loss, 0.469 -> 0.474.)
+    constexpr bool kEcarry = PWS_BWD_ECARRY, kVdup = PWS_BWD_VDUP;
     const unsigned lt = (1u << lane) - 1u;
     int co = -1, eo = -1;        // linear offsets of the parked south-west / south-east sums' targets; -1: nothing parked
     float cv[CS], ev[CS];
@@ -558,7 +567,11 @@ __device__ __forceinline__ void interior_strip_fused(
             float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < CS; ++k) {
+#if PWS_KO & 16
+                const float v0 = go[k], v1 = go[k] + 1.f, v2 = go[k] + 2.f, v3 = go[k] + 3.f; (void)p0;
+#else
                 const float v0 = p0[k * kPlane], v1 = p0[k * kPlane + 1], v2 = p0[k * kPlane + kPitch], v3 = p0[k * kPlane + kPitch + 1];
+#endif
                 const float2 g2 = x2::bc(go[k]);
                 acc = x2::fma(x2::mul(x2::bc(v0), c_nw), g2, acc);
                 acc = x2::fma(x2::mul(x2::bc(v1), c_ne), g2, acc);
@@ -566,7 +579,7 @@ __device__ __forceinline__ void interior_strip_fused(
                 acc = x2::fma(x2::mul(x2::bc(v3), c_se), g2, acc);
             }
             acc = x2::mul(gmul2, acc);
-            tma::st_f32_hint(reinterpret_cast<float *>(gq_x), acc.y, pol_first); tma::st_f32_hint(reinterpret_cast<float *>(gq_y), acc.x, pol_first);
+            if (!(PWS_KO & 4) || __float_as_int(acc.x) == 0x7fc12345) { tma::st_f32_hint(reinterpret_cast<float *>(gq_x), acc.y, pol_first); tma::st_f32_hint(reinterpret_cast<float *>(gq_y), acc.x, pol_first); }
             // (volatile: the unrolled rows otherwise recompute base + r * step with twice the 64-bit adds)
             asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_x) : "l"(gq_step));
             asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_y) : "l"(gq_step));
@@ -574,7 +587,7 @@ __device__ __forceinline__ void interior_strip_fused(
 
         if (kGin) {
             const int o = y0 * W + x0;                      // north-west tap; the others are o + 1, o + W, o + W + 1
-            const int o_left = __shfl_up_sync(0xffffffffu, o, 1);
+            const int o_left = (PWS_KO & 32) ? o - 1 : __shfl_up_sync(0xffffffffu, o, 1);
             // lane l hands its east taps to lane l + 1 when that lane's north-west tap is this lane's north-east one
             // (x0 <= W - 2 in an interior tile: "offset + 1" never wraps into the next row)
             const bool take = lane > 0 && o_left + 1 == o;
@@ -595,7 +608,7 @@ __device__ __forceinline__ void interior_strip_fused(
                 old_e[k] = ev[k];
                 if (e_chain) et[k] += ev[k];                // parked south-east sum: this row's north-east tap
                 if (e_vdup) eb[k] += ev[k];
-                const float pt = __shfl_up_sync(0xffffffffu, et[k], 1), pb = __shfl_up_sync(0xffffffffu, eb[k], 1);
+                const float pt = (PWS_KO & 32) ? et[k] : __shfl_up_sync(0xffffffffu, et[k], 1), pb = (PWS_KO & 32) ? eb[k] : __shfl_up_sync(0xffffffffu, eb[k], 1);
                 if (take) { top += pt; bot += pb; }
                 old_c[k] = cv[k];
                 if (chain) top += cv[k];
@@ -605,10 +618,14 @@ __device__ __forceinline__ void interior_strip_fused(
                 ev[k] = eb[k];
             }
             // stragglers -> queue: the north-east tap nobody took, parked sums whose chain broke
+#if !(PWS_KO & 128)
             if (kEcarry) queue_push<CS>(q, !given, o + 1, et, lt, gp, lane);
             else queue_push2<CS>(q, !given, o + 1, et, o + W + 1, eb, lt, gp, lane);
             queue_push<CS>(q, broke, co, old_c, lt, gp, lane);
             if (kEcarry) queue_push<CS>(q, e_broke, eo, old_e, lt, gp, lane);
+#else
+            if (__float_as_int(old_c[0] + old_e[0] + et[0]) == 0x7fc12345 && (broke || e_broke || !given)) queue_push<CS>(q, true, co, old_c, lt, gp, lane);
+#endif
             co = o + W;
             eo = (kEcarry && !given) ? o + W + 1 : -1;
         }
@@ -761,7 +778,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                     progress_store(&s_progress[warp], max(progress, need));
                     // (the zero-fill warps of a CTA take the bands round-robin: completion is not in order, check every band)
                     for (int b = zero_seen + 1; b <= need; ++b)
-                        while (ld_acquire(&g_zero_done[slot][b]) < gridDim.x) __nanosleep(64);
+                        while (!(PWS_KO & 8) && ld_acquire(&g_zero_done[slot][b]) < gridDim.x) __nanosleep(64);
                     zero_seen = max(zero_seen, need);
                 } else if (kGin) {
                     progress_store(&s_progress[warp], progress);
@@ -792,7 +809,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 float *const fp = (float *)gin.p + (int64_t)(n_begin + f) * gin.sN + (int64_t)r0 * g.W;
                 for (int c = 0; c < CS; ++c) {
                     float4 *__restrict__ dst = reinterpret_cast<float4 *>(fp + c * plane);
-                    for (int v = v0 + lane; v < v1; v += 32) tma::st_zero_v4_hint(dst + v, pol_zero);
+                    for (int v = v0 + lane; v < v1; v += 32) if (!(PWS_KO & 1) || v < 0) tma::st_zero_v4_hint(dst + v, pol_zero);
                 }
 #ifdef PWS_BWD_RELEASE_RED
                 // the warp's stores are ordered before lane 0's release by the warp barrier; the release makes them visible
@@ -841,7 +858,8 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             for (int k = 1; k < CS; ++k) gp[k] = gp[k - 1] + plane_elems;
             float *__restrict__ ggq = kGgrid ? reinterpret_cast<float *>(base.y) + gg_lane : nullptr;
 
-            if (info.z & kInfoInterior) {
+            if ((PWS_KO & 64) && (info.z & kInfoInterior)) {
+            } else if (info.z & kInfoInterior) {
                 // the box address of source pixel (x, y) is bp + y * pitch + x: fold the box origin into the base
                 const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
 #if PWS_BWD_STRIP == 0
