@@ -63,6 +63,36 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+TORCH_EXT = os.path.join(HERE, "_pws_torch.so")
+TORCH_EXT_SRC = os.path.join(CSRC, "torch_binding.cpp")
+
+
+def build_torch_binding(force: bool = False) -> str:
+    """Compile csrc/torch_binding.cpp (host C++ only: the compiled twin of functional.py's ctypes shim, with a C++ autograd
+    node) into pwstablenet_b200/_pws_torch.so, linked against libpwswarp.so next to it.  One g++ call, in-tree."""
+    lib = build_library()
+    deps = [TORCH_EXT_SRC, os.path.join(HERE, "..", "include", "pwswarp.h"), os.path.abspath(__file__)]
+    if not force and os.path.exists(TORCH_EXT) and all(os.path.getmtime(d) <= os.path.getmtime(TORCH_EXT) for d in deps):
+        return TORCH_EXT
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as X
+    inc = X.include_paths("cuda") if "device_type" in X.include_paths.__code__.co_varnames else X.include_paths(True)
+    inc += [sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wno-attributes",
+           "-DTORCH_EXTENSION_NAME=_pws_torch", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI),
+           *["-isystem" + i for i in inc], TORCH_EXT_SRC, "-o", TORCH_EXT,
+           "-L" + tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch", "-ltorch_python",
+           "-L" + HERE, "-l:" + os.path.basename(lib), "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + tlib]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return TORCH_EXT
+
+
 if __name__ == "__main__":
     import sys
     print(build_library(force="-f" in sys.argv, verbose="-v" in sys.argv))
+    print(build_torch_binding(force="-f" in sys.argv))

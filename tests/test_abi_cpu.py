@@ -89,3 +89,17 @@ def test_product_package_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in txt.replace("DESIGN.md", ""), f"{fn} mentions the oracle"
+
+
+def test_compiled_torch_shim_loads_and_binds_the_same_library():
+    """csrc/torch_binding.cpp -> _pws_torch.so: importable without a GPU, linked against the libpwswarp.so next to it."""
+    import importlib
+    from pwstablenet_b200 import _build, _lib
+    _build.build_torch_binding()
+    m = importlib.import_module("pwstablenet_b200._pws_torch")
+    assert m.abi_version() == _lib.ABI_VERSION
+    for name in ("grid_sample", "warp2d_forward", "warp2d_backward"):
+        assert callable(getattr(m, name))
+    maps = open("/proc/self/maps").read()
+    assert maps.count(os.path.join("pwstablenet_b200", "libpwswarp.so")) > 0
+    assert len({l.split()[-1] for l in maps.splitlines() if l.endswith("libpwswarp.so")}) == 1   # one copy, not two

@@ -14,7 +14,11 @@ def step(fn, n):
         y.backward(y.detach())
         x.grad = None; g.grad = None
 
-for name, fn in (("torch", F.grid_sample), ("ours", pw.grid_sample)):
+from pwstablenet_b200 import functional as PF
+def ctypes_shim(x, g, align_corners=False):
+    return PF._Warp2d.apply(x, g, 0, align_corners)
+print("compiled shim:", bool(PF.torch_ext()))
+for name, fn in (("torch", F.grid_sample), ("ours", pw.grid_sample), ("ours, ctypes shim", ctypes_shim)):
     step(fn, 50); torch.cuda.synchronize()
     t0 = time.perf_counter(); step(fn, 500); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
     print(f"{name}: host {1e6 * (t1 - t0) / 500:.1f} us per forward+backward (GPU drained {1e6 * (t2 - t1):.0f} us after the loop)")
