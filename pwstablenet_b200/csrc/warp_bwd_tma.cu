@@ -52,7 +52,13 @@ namespace {
 #ifndef PWS_BWD_VDUP
 #define PWS_BWD_VDUP 1
 #endif
-constexpr int kScouts = 2, kGroups = 2, kGroupWarps = 8, kConsumers = kGroups * kGroupWarps;
+#ifndef PWS_BWD_GGRID_EXACT   // 1: grad_grid of interior tiles in ATen's statement order (bit-identical to it); 0: factored form --
+#define PWS_BWD_GGRID_EXACT 1 // 22 operations per pixel instead of 48, and not one microsecond faster: not the product
+#endif
+#ifndef PWS_BWD_GROUPS   // consumer groups of 8 warps, one scout each (2; 1 for the scaling experiment of DESIGN 3.3)
+#define PWS_BWD_GROUPS 2
+#endif
+constexpr int kScouts = PWS_BWD_GROUPS, kGroups = PWS_BWD_GROUPS, kGroupWarps = 8, kConsumers = kGroups * kGroupWarps;
 // The zero-fill of grad_input paces the whole kernel when ONE warp does it: a band costs that warp its stores plus a
 // gpu-scope fence (~2 us while the REDs keep the memory system busy), 128 bands of a 16-frame launch = the kernel's 0.46 ms
 // (ncu: the zero-fill warp never sleeps, half of its samples sit on the fence).  kZeroWarps warps take the bands round-robin.
@@ -562,6 +568,7 @@ __device__ __forceinline__ void interior_strip_fused(
 
         if (kGgrid) {
             const float *__restrict__ p0 = bp + (y0 * kPitch + x0);
+#if PWS_BWD_GGRID_EXACT
             // per tap the weights of (giy, gix) with ATen's signs: nw (-dw, -dn), ne (-de, +dn), sw (+dw, -ds), se (+de, +ds)
             const float2 c_nw = make_float2(-dw, -dn), c_ne = make_float2(-de, dn), c_sw = make_float2(dw, -ds), c_se = es;
             float2 acc = make_float2(0.f, 0.f);
@@ -579,6 +586,28 @@ __device__ __forceinline__ void interior_strip_fused(
                 acc = x2::fma(x2::mul(x2::bc(v3), c_se), g2, acc);
             }
             acc = x2::mul(gmul2, acc);
+#else
+            // grad_grid through the channel sums of the four taps: S_t = sum_k go_k * v_t,k (12 multiply-adds), then
+            //   giy = gym * (dw * (S_sw - S_nw) + de * (S_se - S_ne)),  gix = gxm * (dn * (S_ne - S_nw) + ds * (S_se - S_sw))
+            // -- 22 scalar operations per pixel where ATen's statement order (the EXACT build) takes 48 (25 packed pairs, which
+            // issue at half rate).  Same real-number value; the rounding differs in the last bits (measured 2.4e-7 of the
+            // largest |grad_grid| at 1080p, the size of ATen's own rounding noise: both sum signed terms of the taps' magnitude).
+            float s_nw, s_ne, s_sw, s_se;
+#pragma unroll
+            for (int k = 0; k < CS; ++k) {
+#if PWS_KO & 16
+                const float v0 = go[k], v1 = go[k] + 1.f, v2 = go[k] + 2.f, v3 = go[k] + 3.f; (void)p0;
+#else
+                const float v0 = p0[k * kPlane], v1 = p0[k * kPlane + 1], v2 = p0[k * kPlane + kPitch], v3 = p0[k * kPlane + kPitch + 1];
+#endif
+                if (k == 0) { s_nw = fmul(go[0], v0); s_ne = fmul(go[0], v1); s_sw = fmul(go[0], v2); s_se = fmul(go[0], v3); }
+                else { s_nw = fmaf(go[k], v0, s_nw); s_ne = fmaf(go[k], v1, s_ne); s_sw = fmaf(go[k], v2, s_sw); s_se = fmaf(go[k], v3, s_se); }
+            }
+            float2 acc;
+            acc.x = fmaf(de, s_se - s_ne, fmul(dw, s_sw - s_nw));
+            acc.y = fmaf(ds, s_se - s_sw, fmul(dn, s_ne - s_nw));
+            acc.x = fmul(gmul2.x, acc.x); acc.y = fmul(gmul2.y, acc.y);
+#endif
             if (!(PWS_KO & 4) || __float_as_int(acc.x) == 0x7fc12345) { tma::st_f32_hint(reinterpret_cast<float *>(gq_x), acc.y, pol_first); tma::st_f32_hint(reinterpret_cast<float *>(gq_y), acc.x, pol_first); }
             // (volatile: the unrolled rows otherwise recompute base + r * step with twice the 64-bit adds)
             asm volatile("add.s64 %0, %0, %1;" : "+l"(gq_x) : "l"(gq_step));
