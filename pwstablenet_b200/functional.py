@@ -226,23 +226,63 @@ def warp_taps(grid: torch.Tensor, in_h: int, in_w: int, padding_mode: str = "zer
 
 
 _torch_grid_sample = None
+_aten_lib = None
 
 
-def install() -> None:
+def _aten_grid_sampler_2d(input, grid, interpolation_mode, padding_mode, align_corners):
+    """CUDA kernel of aten::grid_sampler_2d ($TORCH/include/ATen/native/cuda/GridSampler.h:12-17) while the override is installed."""
+    if interpolation_mode != 0 or padding_mode not in (0, 1):
+        raise NotImplementedError("pwstablenet_b200 (aten override): bilinear with zeros / border padding only; "
+                                  "uninstall() the override for nearest / bicubic / reflection")
+    ext = _ext if _ext is not None else torch_ext()
+    if ext:
+        return ext.warp2d_forward(input, grid, int(padding_mode), bool(align_corners))
+    return warp2d_forward(input, grid, int(padding_mode), bool(align_corners))
+
+
+def _aten_grid_sampler_2d_backward(grad_output, input, grid, interpolation_mode, padding_mode, align_corners, output_mask):
+    """CUDA kernel of aten::grid_sampler_2d_backward (GridSampler.h:19-24).  ATen returns an undefined grad_input when
+    output_mask[0] is false; a Python kernel cannot, it returns an empty tensor (autograd does not look at it)."""
+    if interpolation_mode != 0 or padding_mode not in (0, 1):
+        raise NotImplementedError("pwstablenet_b200 (aten override): bilinear with zeros / border padding only")
+    gin, ggrid = warp2d_backward(grad_output, input, grid, int(padding_mode), bool(align_corners), (bool(output_mask[0]), True))
+    if gin is None:
+        gin = input.new_empty(0)
+    return gin, ggrid
+
+
+def install(aten_override: bool = False) -> None:
     """Route torch.nn.functional.grid_sample to this implementation so the reference's
     main_new.py / main.py run unmodified (they call `functional.grid_sample(...)` /
-    `F.grid_sample(...)` through the module attribute)."""
-    global _torch_grid_sample
+    `F.grid_sample(...)` through the module attribute).
+
+    aten_override=True additionally registers the two C-ABI entry points as the CUDA kernels of aten::grid_sampler_2d and
+    aten::grid_sampler_2d_backward (SURVEY 8(b): the optional torch.library override), for callers that hold their own
+    reference to torch's function or reach the operator some other way (torch.grid_sampler, a scripted module).  The
+    operator keeps ATen's autograd formula; only the kernels underneath change.  (torch routes bilinear + zeros +
+    align_corners=True through cuDNN ABOVE this operator; the functional-level patch covers that case, the override alone
+    does not.)"""
+    global _torch_grid_sample, _aten_lib
     import torch.nn.functional as F
     _lib.load()
     if _torch_grid_sample is None:
         _torch_grid_sample = F.grid_sample
         F.grid_sample = grid_sample
+    if aten_override and _aten_lib is None:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")      # "Overriding a previously registered kernel": that is the point
+            lib = torch.library.Library("aten", "IMPL")
+            lib.impl("grid_sampler_2d", _aten_grid_sampler_2d, "CUDA")
+            lib.impl("grid_sampler_2d_backward", _aten_grid_sampler_2d_backward, "CUDA")
+        _aten_lib = lib
 
 
 def uninstall() -> None:
-    global _torch_grid_sample
+    global _torch_grid_sample, _aten_lib
     import torch.nn.functional as F
     if _torch_grid_sample is not None:
         F.grid_sample = _torch_grid_sample
         _torch_grid_sample = None
+    if _aten_lib is not None:
+        _aten_lib._destroy()     # drops the two registrations: ATen's own CUDA kernels are back
+        _aten_lib = None

@@ -81,3 +81,35 @@ def test_ext_errors(pw):
         ext.warp2d_forward(f, g, 2, False)            # reflection padding: outside this library's scope
     with pytest.raises(RuntimeError):
         ext.warp2d_forward(f, g[..., :1], 0, False)   # grid.size(-1) != 2
+
+
+def test_aten_override_routes_the_operator_itself(pw):
+    """install(aten_override=True): aten::grid_sampler_2d{,_backward} on CUDA are the C-ABI entry points, reached here through
+    torch.grid_sampler (no Python patch involved); ATen's autograd formula drives the backward.  uninstall() restores ATen."""
+    f, g, go = _inputs(2, 3, 96, 128)
+    fa, ga = f.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    ref = pw.grid_sample(fa, ga, padding_mode="border", align_corners=False)
+    ref.backward(go)
+    pw.install(aten_override=True)
+    try:
+        fb, gb = f.clone().requires_grad_(True), g.clone().requires_grad_(True)
+        l0 = pw._lib.launch_count()
+        out = torch.grid_sampler(fb, gb, 0, 1, False)
+        assert pw._lib.launch_count() > l0, "the operator did not reach libpwswarp.so"
+        assert torch.equal(out, ref)
+        l1 = pw._lib.launch_count()
+        out.backward(go)
+        assert pw._lib.launch_count() > l1
+        assert torch.equal(gb.grad, ga.grad)
+        assert (fb.grad - fa.grad).abs().max().item() <= 1e-4 * fa.grad.abs().max().item()
+        gc = g.clone().requires_grad_(True)
+        torch.grid_sampler(f, gc, 0, 0, False).backward(go)          # output_mask (False, True)
+        assert gc.grad is not None
+        with pytest.raises(NotImplementedError):
+            torch.grid_sampler(f, g, 1, 0, False)                    # nearest: outside the library's scope, no fallback
+    finally:
+        pw.uninstall()
+    l2 = pw._lib.launch_count()
+    out2 = torch.grid_sampler(f, g, 0, 1, False)                     # ATen's own kernel again
+    assert pw._lib.launch_count() == l2
+    assert torch.allclose(out2, ref.detach(), atol=1e-3, rtol=1e-5)
