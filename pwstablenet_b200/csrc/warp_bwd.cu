@@ -264,6 +264,17 @@ int launch_typed(const Problem &pb, cudaStream_t st)
 // pixel's contributions in bf16 would round after every atomic.
 int launch_16bit(const Problem &pb, cudaStream_t st)
 {
+    // above the small-problem threshold: the persistent TMA kernel with 16-bit grad_output tiles and frame boxes (RGB only)
+    if (!force_generic() && !small_problem(pb)) {
+        BwdTmaPlan *plan = backward_tma_plan(pb);
+        struct PlanGuard { BwdTmaPlan *p; ~PlanGuard() { if (p) backward_tma_free(p); } } plan_guard{plan};
+        if (plan) {
+            const int step = backward_tma_max_frames();
+            bool ok = true;
+            for (int n0 = 0; ok && n0 < pb.g.N; n0 += step) ok = launch_backward_tma(plan, pb, n0, pb.g.N - n0 < step ? pb.g.N - n0 : step, st);
+            if (ok) return PWS_OK;
+        }
+    }
     if (!backward_lean_eligible(pb)) {
         set_error("backward: 16-bit frames need W-contiguous frames / grad_output, C in {1,3} and an fp32 map");
         return PWS_EUNSUPPORTED;

@@ -97,7 +97,7 @@ constexpr int kSyncSlots = kLaunchSlots, kSyncFrames = 256;
 // Every band costs its CTA's zero-fill warp a fence, an atomic and a poll (~1 us): a launch of many SMALL frames must not pay
 // eight of them per frame, so the number of bands per frame follows the frame size (about 4 MB of grad_input per band,
 // 1..kMaxBands).
-constexpr int kMaxBands = 8;
+constexpr int kMaxBands = 32;   // (a 4K fp32 grad_input frame is 25 bands of 4 MB)
 __device__ unsigned int g_zero_done[kSyncSlots][kSyncFrames * kMaxBands];
 __device__ unsigned int g_exit_count[kSyncSlots];
 // Tiles are handed out dynamically: the SMs of a B200 do not run this kernel at the same pace (the spread is several
@@ -141,11 +141,12 @@ constexpr int kSlotShape = PWS_BWD_SLOT_SHAPE;
 // and one `empty` mbarrier.  The map tiles live in a ring of their own that is two slots deeper: a scout loads the
 // map of its NEXT tile while it dispatches the current one, so that the bounding box of a tile is known before the
 // tile's stage frees up and the grad_output and box loads leave the moment it does.
-template <int CS, bool kGgrid> struct Smem {
-    static constexpr int kStages = kGgrid ? PWS_BWD_STAGES : 6;
+// kElem: bytes per frame / grad_output element (4, or 2 for f16 / bf16 frames: the smaller stages buy a deeper ring)
+template <int CS, bool kGgrid, int kElem = 4> struct Smem {
+    static constexpr int kStages = kGgrid ? (kElem == 2 ? 6 : PWS_BWD_STAGES) : 6;
     static constexpr int kMapStages = kStages + kScouts;
-    static constexpr int kGoutBytes = CS * kTW * kTH * 4;
-    static constexpr int kBoxBytes = kGgrid ? (box_w(kSlotShape) * box_h(kSlotShape) * CS * 4 + 127) / 128 * 128 : 0;
+    static constexpr int kGoutBytes = CS * kTW * kTH * kElem;
+    static constexpr int kBoxBytes = kGgrid ? (box_w(kSlotShape) * box_h(kSlotShape) * CS * kElem + 127) / 128 * 128 : 0;
     static constexpr int kMapOff = 0;
     static constexpr int kGoutOff = kMapStages * kMapTileBytes;
     static constexpr int kBoxOff = kGoutOff + kStages * kGoutBytes;
@@ -235,13 +236,13 @@ __device__ __forceinline__ void queue_flush(Queue<CS> &q, float *const (&gp)[CS]
 // One output row (32 pixels) of a warp in a tile that is NOT interior (frame border, partial tile, no box): every tap and
 // every lane is checked.  kBoxTaps: the taps of grad_grid come from the shared-memory box
 // (tap = box[(y - by) * pitch + (x - bx)] per plane), else from global memory.
-template <int CS, bool kGin, bool kGgrid, bool kBoxTaps>
+template <typename T, int CS, bool kGin, bool kGgrid, bool kBoxTaps>
 __device__ __forceinline__ void masked_row(
     const int lane, const bool px_ok, const unsigned live,
     const float ix, const float iy, const float x0f, const float y0f, const int x0, const int y0,
     const float gxm, const float gym, const float (&go)[CS],
-    const float *__restrict__ box, const int pitch, const int plane,
-    const float *__restrict__ ip, const int sH, const int i_ch, const int H, const int W,
+    const T *__restrict__ box, const int pitch, const int plane,
+    const T *__restrict__ ip, const int sH, const int i_ch, const int H, const int W,
     float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s3, Carry<CS> &cy, Queue<CS> &q, const uint64_t pol_first)
 {
     const float dw = fsub(x0f + 1.0f, ix), de = fsub(ix, x0f), dn = fsub(y0f + 1.0f, iy), ds = fsub(iy, y0f);
@@ -252,22 +253,22 @@ __device__ __forceinline__ void masked_row(
 
     if (kGgrid && px_ok) {
         float gix = 0.f, giy = 0.f;
-        const float *__restrict__ p0 = kBoxTaps ? box + (y0 * pitch + x0) : ip + (y0 * sH + x0);
+        const T *__restrict__ p0 = kBoxTaps ? box + (y0 * pitch + x0) : ip + (y0 * sH + x0);
         const int row = kBoxTaps ? pitch : sH, ch = kBoxTaps ? plane : i_ch;
 #pragma unroll
         for (int k = 0; k < CS; ++k) {
-            const float *__restrict__ pc = p0 + k * ch;
+            const T *__restrict__ pc = p0 + k * ch;
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
             if (kBoxTaps) {
-                if (mask & 1u) v0 = pc[0];
-                if (mask & 2u) v1 = pc[1];
-                if (mask & 4u) v2 = pc[row];
-                if (mask & 8u) v3 = pc[row + 1];
+                if (mask & 1u) v0 = to_acc(pc[0]);
+                if (mask & 2u) v1 = to_acc(pc[1]);
+                if (mask & 4u) v2 = to_acc(pc[row]);
+                if (mask & 8u) v3 = to_acc(pc[row + 1]);
             } else {
-                if (mask & 1u) v0 = __ldg(pc);
-                if (mask & 2u) v1 = __ldg(pc + 1);
-                if (mask & 4u) v2 = __ldg(pc + row);
-                if (mask & 8u) v3 = __ldg(pc + row + 1);
+                if (mask & 1u) v0 = to_acc(__ldg(pc));
+                if (mask & 2u) v1 = to_acc(__ldg(pc + 1));
+                if (mask & 4u) v2 = to_acc(__ldg(pc + row));
+                if (mask & 8u) v3 = to_acc(__ldg(pc + row + 1));
             }
             // ATen's statement order: t = v*d rounded, then one fma with gOut
             if (mask & 1u) { gix = ffma(-fmul(v0, dn), go[k], gix); giy = ffma(-fmul(v0, dw), go[k], giy); }
@@ -325,11 +326,11 @@ __device__ __forceinline__ void masked_row(
 }
 
 // A strip of a tile that is not "interior": the masked rows, then the parked south-west sums.
-template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
+template <typename T, int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 __device__ __forceinline__ void masked_strip(
     const int lane, const int4 info, const int h0, const int w0, const int row0, const int col0,
-    const float *__restrict__ mp, const float *__restrict__ gop, const float *__restrict__ bp, const int pitch, const int plane,
-    const float *__restrict__ ip, const int sH, const int i_ch, const Geometry g,
+    const float *__restrict__ mp, const T *__restrict__ gop, const T *__restrict__ bp, const int pitch, const int plane,
+    const T *__restrict__ ip, const int sH, const int i_ch, const Geometry g,
     float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Queue<CS> &q, const uint64_t pol_first)
 {
     const float Wf = (float)g.W, Hf = (float)g.H, Wm1 = (float)(g.W - 1), Hm1 = (float)(g.H - 1);
@@ -346,17 +347,17 @@ __device__ __forceinline__ void masked_strip(
         if (kInter) { const float2 v = *reinterpret_cast<const float2 *>(mp + (row0 + r) * (2 * kTW) + 2 * (col0 + lane)); gx = v.x; gy = v.y; }
         else { gx = mp[(row0 + r) * kTW + col0 + lane]; gy = mp[kTW * kTH + (row0 + r) * kTW + col0 + lane]; }
 #pragma unroll
-        for (int k = 0; k < CS; ++k) go[k] = gop[k * (kTW * kTH) + r * kTW];
+        for (int k = 0; k < CS; ++k) go[k] = to_acc(gop[k * (kTW * kTH) + r * kTW]);
         float gxm, gym;
         const float ix = src_index_grad<kBorder, kAlign>(gx, Wf, Wm1, &gxm);
         const float iy = src_index_grad<kBorder, kAlign>(gy, Hf, Hm1, &gym);
         const float x0f = floorf(ix), y0f = floorf(iy);
         const int x0 = (int)x0f, y0 = (int)y0f;
         if (box_taps)
-            masked_row<CS, kGin, kGgrid, true>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
+            masked_row<T, CS, kGin, kGgrid, true>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
                                                bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gp, ggq, gg_s3, cy, q, pol_first);
         else
-            masked_row<CS, kGin, kGgrid, false>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
+            masked_row<T, CS, kGin, kGgrid, false>(lane, col_ok, live, ix, iy, x0f, y0f, x0, y0, gxm, gym, go,
                                                 bp, pitch, plane, ip, sH, i_ch, g.H, g.W, gp, ggq, gg_s3, cy, q, pol_first);
         if (kGgrid) ggq += gg_s1;
     }
@@ -527,10 +528,10 @@ __device__ __forceinline__ void interior_strip(
 
 // The same strip with grad_grid and the scatter of a row fused in one body (one pass over the map and grad_output in shared
 // memory; fewer instructions than the two-phase form, longer dependent chains).  The product form.
-template <int CS, bool kAlign, bool kInter, bool kGin, bool kGgrid, int SHAPE>
+template <typename T, int CS, bool kAlign, bool kInter, bool kGin, bool kGgrid, int SHAPE>
 __device__ __forceinline__ void interior_strip_fused(
     const int lane, const float *__restrict__ mq /* this lane's map element(s) in the strip's first row */,
-    const float *__restrict__ gop, const float *__restrict__ bp, const int pitch_rt, const int plane_rt,
+    const T *__restrict__ gop, const T *__restrict__ bp, const int pitch_rt, const int plane_rt,
     const float2 size2 /* (W, H) as floats; (W-1, H-1) when kAlign */, const int W, const float2 gmul2 /* (gym, gxm) */,
     float *const (&gp)[CS], float *__restrict__ ggq, const int gg_s1, const int gg_s3, Queue<CS> &q, const uint64_t pol_first)
 {
@@ -556,7 +557,7 @@ __device__ __forceinline__ void interior_strip_fused(
         else { gxy.x = mq[r * kTW]; gxy.y = mq[kTW * kTH + r * kTW]; }
         float go[CS];
 #pragma unroll
-        for (int k = 0; k < CS; ++k) go[k] = gop[k * (kTW * kTH) + r * kTW];
+        for (int k = 0; k < CS; ++k) go[k] = to_acc(gop[k * (kTW * kTH) + r * kTW]);
         // unnormalise (ATen's operation order), floor, fractions
         const float2 t = x2::add(gxy, x2::bc(1.0f));
         const float2 ixy = kAlign ? x2::mul(x2::mul(t, x2::bc(0.5f)), size2) : x2::mul(x2::fma(t, size2, x2::bc(-1.0f)), x2::bc(0.5f));
@@ -567,7 +568,7 @@ __device__ __forceinline__ void interior_strip_fused(
         const float de = es.x, ds = es.y, dw = wn.x, dn = wn.y;
 
         if (kGgrid) {
-            const float *__restrict__ p0 = bp + (y0 * kPitch + x0);
+            const T *__restrict__ p0 = bp + (y0 * kPitch + x0);
 #if PWS_BWD_GGRID_EXACT
             // per tap the weights of (giy, gix) with ATen's signs: nw (-dw, -dn), ne (-de, +dn), sw (+dw, -ds), se (+de, +ds)
             const float2 c_nw = make_float2(-dw, -dn), c_ne = make_float2(-de, dn), c_sw = make_float2(dw, -ds), c_se = es;
@@ -577,7 +578,7 @@ __device__ __forceinline__ void interior_strip_fused(
 #if PWS_KO & 16
                 const float v0 = go[k], v1 = go[k] + 1.f, v2 = go[k] + 2.f, v3 = go[k] + 3.f; (void)p0;
 #else
-                const float v0 = p0[k * kPlane], v1 = p0[k * kPlane + 1], v2 = p0[k * kPlane + kPitch], v3 = p0[k * kPlane + kPitch + 1];
+                const float v0 = to_acc(p0[k * kPlane]), v1 = to_acc(p0[k * kPlane + 1]), v2 = to_acc(p0[k * kPlane + kPitch]), v3 = to_acc(p0[k * kPlane + kPitch + 1]);
 #endif
                 const float2 g2 = x2::bc(go[k]);
                 acc = x2::fma(x2::mul(x2::bc(v0), c_nw), g2, acc);
@@ -598,7 +599,7 @@ __device__ __forceinline__ void interior_strip_fused(
 #if PWS_KO & 16
                 const float v0 = go[k], v1 = go[k] + 1.f, v2 = go[k] + 2.f, v3 = go[k] + 3.f; (void)p0;
 #else
-                const float v0 = p0[k * kPlane], v1 = p0[k * kPlane + 1], v2 = p0[k * kPlane + kPitch], v3 = p0[k * kPlane + kPitch + 1];
+                const float v0 = to_acc(p0[k * kPlane]), v1 = to_acc(p0[k * kPlane + 1]), v2 = to_acc(p0[k * kPlane + kPitch]), v3 = to_acc(p0[k * kPlane + kPitch + 1]);
 #endif
                 if (k == 0) { s_nw = fmul(go[0], v0); s_ne = fmul(go[0], v1); s_sw = fmul(go[0], v2); s_se = fmul(go[0], v3); }
                 else { s_nw = fmaf(go[k], v0, s_nw); s_ne = fmaf(go[k], v1, s_ne); s_sw = fmaf(go[k], v2, s_sw); s_se = fmaf(go[k], v3, s_se); }
@@ -666,12 +667,12 @@ __device__ __forceinline__ void interior_strip_fused(
     }
 }
 
-template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
+template <typename T, int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 __global__ void __launch_bounds__(kThreads, 1)
 bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View grid, const View gin, const View ggrid, const Geometry g,
                const int tiles_x, const int tiles_y, const int total_tiles, const int n_begin, const int n_frames, const int slot, const int kBands)
 {
-    using S = Smem<CS, kGgrid>;
+    using S = Smem<CS, kGgrid, (int)sizeof(T)>;
     constexpr int kStages = S::kStages, kMapStages = S::kMapStages;
     extern __shared__ __align__(1024) unsigned char smem[];
     float *const s_map = reinterpret_cast<float *>(smem + S::kMapOff);
@@ -767,7 +768,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             tma::mbar_wait_relaxed(map_full + ms, mph);
             float xlo, xhi, ylo, yhi;
             map_tile_range<kInter>(s_map + ms * kMapTileFloats, rows, cols, lane, xlo, xhi, ylo, yhi);
-            int4 info = box_of_range<kBorder, kAlign>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
+            int4 info = box_of_range<kBorder, kAlign, false, 16 / (int)sizeof(T)>(xlo, xhi, ylo, yhi, g.W, g.H, cols == kTW && rows == kTH);
             if (kGgrid && kSlotShape < kNumShapes - 1 && !(info.z & (kInfoFallback | kInfoEmpty)) && (info.z & 0xff) > kSlotShape)
                 info = make_int4(0, 0, kInfoFallback, 0);
             info.w = tc.n;
@@ -795,7 +796,7 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                                                                                                (int64_t)tc.h0 * ggrid.s1 + (int64_t)tc.w0 * ggrid.s2)) : 0;
                     reinterpret_cast<ulonglong2 *>(s_info)[3 * st + 2] = make_ulonglong2(p_gin, p_gg);
                 }
-                tma::mbar_arrive_expect_tx(full + st, S::kGoutBytes + (want_box ? box_w(shape) * box_h(shape) * CS * 4 : 0));
+                tma::mbar_arrive_expect_tx(full + st, S::kGoutBytes + (want_box ? box_w(shape) * box_h(shape) * CS * (int)sizeof(T) : 0));
                 tma::load_4d_hint(s_gout + (size_t)st * S::kGoutBytes, &tp.gout, full + st, tc.w0, tc.h0, 0, n_begin + tc.n, pol_first);
                 if (want_box) tma::load_4d_hint(s_box + (size_t)st * S::kBoxBytes, &tp.box[shape], full + st, info.x, info.y, 0, n_begin + tc.n, pol_box);
                 if (kGin && !(info.z & kInfoEmpty)) {
@@ -877,8 +878,8 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
             const int shape = info.z & 0xff;
             const int ms = it % kMapStages;
             const float *mp = s_map + ms * kMapTileFloats;
-            const float *gop = reinterpret_cast<const float *>(s_gout + (size_t)is * S::kGoutBytes) + gout_lane;
-            const float *box0 = reinterpret_cast<const float *>(s_box + (size_t)is * S::kBoxBytes);
+            const T *gop = reinterpret_cast<const T *>(s_gout + (size_t)is * S::kGoutBytes) + gout_lane;
+            const T *box0 = reinterpret_cast<const T *>(s_box + (size_t)is * S::kBoxBytes);
             // this frame's grad_input planes: one 64-bit base per channel, source pixels are 32-bit offsets from them
             const ulonglong2 base = reinterpret_cast<const ulonglong2 *>(s_info)[3 * is + 2];   // published by the scout
             float *gp[CS];
@@ -892,22 +893,23 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
                 // the box address of source pixel (x, y) is bp + y * pitch + x: fold the box origin into the base
                 const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
 #if PWS_BWD_STRIP == 0
+                static_assert(sizeof(T) == 4, "the two-phase strip is fp32-only");
                 interior_strip<CS, kAlign, kInter, kGin, kGgrid>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane,
                                                                  size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
 #elif PWS_BWD_STRIP == 1
-                interior_strip_fused<CS, kAlign, kInter, kGin, kGgrid, -1>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane,
+                interior_strip_fused<T, CS, kAlign, kInter, kGin, kGgrid, -1>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane,
                                                                            size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
 #else
                 switch (shape) {
-                case 0: interior_strip_fused<CS, kAlign, kInter, kGin, kGgrid, 0>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane, size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg); break;
-                case 1: interior_strip_fused<CS, kAlign, kInter, kGin, kGgrid, 1>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane, size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg); break;
-                default: interior_strip_fused<CS, kAlign, kInter, kGin, kGgrid, 2>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane, size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg); break;
+                case 0: interior_strip_fused<T, CS, kAlign, kInter, kGin, kGgrid, 0>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane, size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg); break;
+                case 1: interior_strip_fused<T, CS, kAlign, kInter, kGin, kGgrid, 1>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane, size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg); break;
+                default: interior_strip_fused<T, CS, kAlign, kInter, kGin, kGgrid, 2>(lane, mp + map_lane, gop, box0 - (info.y * pitch + info.x), pitch, plane, size2, g.W, gmul2, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg); break;
                 }
 #endif
             } else {
                 const int pitch = box_w(shape), plane = box_w(shape) * box_h(shape);
-                const float *__restrict__ ip = (const float *)in.p + (int64_t)n * in.sN;
-                masked_strip<CS, kBorder, kAlign, kInter, kGin, kGgrid>(lane, info, where.x + row0, where.y + col0, row0, col0, mp, gop,
+                const T *__restrict__ ip = (const T *)in.p + (int64_t)n * in.sN;
+                masked_strip<T, CS, kBorder, kAlign, kInter, kGin, kGgrid>(lane, info, where.x + row0, where.y + col0, row0, col0, mp, gop,
                                                                         box0 - (info.y * pitch + info.x), pitch, plane, ip, in.s2, in.s1,
                                                                         g, gp, ggq, ggrid.s1, ggrid.s3, q, pol_gg);
             }
@@ -929,11 +931,11 @@ bwd_tma_kernel(const __grid_constant__ TmaParams tp, const View in, const View g
     }
 }
 
-template <int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
+template <typename T, int CS, bool kBorder, bool kAlign, bool kInter, bool kGin, bool kGgrid>
 bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, int total, int n0, cudaStream_t st)
 {
-    auto kern = bwd_tma_kernel<CS, kBorder, kAlign, kInter, kGin, kGgrid>;
-    using S = Smem<CS, kGgrid>;
+    auto kern = bwd_tma_kernel<T, CS, kBorder, kAlign, kInter, kGin, kGgrid>;
+    using S = Smem<CS, kGgrid, (int)sizeof(T)>;
     static std::atomic<uint64_t> attr_done{0};  // per instantiation, one bit per device
     if (!ensure_dynamic_smem(reinterpret_cast<const void *>(kern), S::kTotal, attr_done)) return false;
     const int grid = total < sm_count() ? total : sm_count();
@@ -961,26 +963,26 @@ bool launch_k(const TmaParams &tp, const Problem &pb, int tiles_x, int tiles_y, 
         return false;
     }
     note_launch();
-    note_kernel("bwd_tma");
+    note_kernel(sizeof(T) == 2 ? "bwd_tma_16" : "bwd_tma");
     return true;
 }
 
-template <int CS, bool kBorder, bool kAlign, bool kInter>
+template <typename T, int CS, bool kBorder, bool kAlign, bool kInter>
 bool launch_mask(const TmaParams &tp, const Problem &pb, int tx, int ty, int total, int n0, cudaStream_t st)
 {
-    if (pb.want_gin && pb.want_ggrid) return launch_k<CS, kBorder, kAlign, kInter, true, true>(tp, pb, tx, ty, total, n0, st);
-    if (pb.want_gin) return launch_k<CS, kBorder, kAlign, kInter, true, false>(tp, pb, tx, ty, total, n0, st);
-    return launch_k<CS, kBorder, kAlign, kInter, false, true>(tp, pb, tx, ty, total, n0, st);
+    if (pb.want_gin && pb.want_ggrid) return launch_k<T, CS, kBorder, kAlign, kInter, true, true>(tp, pb, tx, ty, total, n0, st);
+    if (pb.want_gin) return launch_k<T, CS, kBorder, kAlign, kInter, true, false>(tp, pb, tx, ty, total, n0, st);
+    return launch_k<T, CS, kBorder, kAlign, kInter, false, true>(tp, pb, tx, ty, total, n0, st);
 }
 
-template <int CS, bool kInter>
+template <typename T, int CS, bool kInter>
 bool launch_ba(const TmaParams &tp, const Problem &pb, int tx, int ty, int total, int n0, cudaStream_t st)
 {
     const bool border = pb.g.padding == PWS_PAD_BORDER, align = pb.g.align != 0;
-    if (border && align) return launch_mask<CS, true, true, kInter>(tp, pb, tx, ty, total, n0, st);
-    if (border) return launch_mask<CS, true, false, kInter>(tp, pb, tx, ty, total, n0, st);
-    if (align) return launch_mask<CS, false, true, kInter>(tp, pb, tx, ty, total, n0, st);
-    return launch_mask<CS, false, false, kInter>(tp, pb, tx, ty, total, n0, st);
+    if (border && align) return launch_mask<T, CS, true, true, kInter>(tp, pb, tx, ty, total, n0, st);
+    if (border) return launch_mask<T, CS, true, false, kInter>(tp, pb, tx, ty, total, n0, st);
+    if (align) return launch_mask<T, CS, false, true, kInter>(tp, pb, tx, ty, total, n0, st);
+    return launch_mask<T, CS, false, false, kInter>(tp, pb, tx, ty, total, n0, st);
 }
 
 }  // namespace
@@ -997,8 +999,10 @@ BwdTmaPlan *backward_tma_plan(const Problem &pb)
 {
     const Geometry &g = pb.g;
     if (tma_disabled()) return nullptr;
-    if (pb.in_dtype != PWS_F32 || pb.grid_dtype != PWS_F32) return nullptr;
-    if (g.C != 1 && g.C != 3) return nullptr;
+    if (pb.grid_dtype != PWS_F32) return nullptr;
+    const bool half_frames = pb.in_dtype == PWS_F16 || pb.in_dtype == PWS_BF16;   // grad_output has the frames' type, grad_input is fp32
+    if (pb.in_dtype != PWS_F32 && !half_frames) return nullptr;
+    if (half_frames ? g.C != 3 : (g.C != 1 && g.C != 3)) return nullptr;   // (16-bit: the RGB instantiations only)
     if (g.W > (1 << 22) || g.H > (1 << 22)) return nullptr;
     if (pb.want_gin && !(pb.gin.s3 == 1 && pb.gin.s2 == g.W && pb.gin.s1 == g.W * g.H)) return nullptr;
     // in-kernel zero-fill writes float4: frame base and frame stride 16-byte aligned
@@ -1012,8 +1016,8 @@ BwdTmaPlan *backward_tma_plan(const Problem &pb)
     pl->tiles_x = (g.Wo + kTW - 1) / kTW;
     pl->tiles_y = (g.Ho + kTH - 1) / kTH;
     bool ok = encode_map_tma(pb.grid, g, &pl->tp.map, &pl->inter);
-    ok = ok && encode_frame_tma(pb.gout, g.Wo, g.Ho, g.C, g.N, kTW, kTH, g.C, &pl->tp.gout);
-    for (int s = 0; ok && s < kNumShapes; ++s) ok = encode_frame_tma(pb.in, g.W, g.H, g.C, g.N, box_w(s), box_h(s), g.C, &pl->tp.box[s]);
+    ok = ok && encode_frame_tma(pb.gout, g.Wo, g.Ho, g.C, g.N, kTW, kTH, g.C, &pl->tp.gout, pb.in_dtype);
+    for (int s = 0; ok && s < kNumShapes; ++s) ok = encode_frame_tma(pb.in, g.W, g.H, g.C, g.N, box_w(s), box_h(s), g.C, &pl->tp.box[s], pb.in_dtype);
     if ((int64_t)pl->tiles_x * pl->tiles_y * g.N > INT_MAX) ok = false;
     if (!ok) { delete pl; return nullptr; }
     return pl;
@@ -1028,11 +1032,17 @@ bool launch_backward_tma(const BwdTmaPlan *pl, const Problem &pb, int n0, int nn
 {
     const int total = pl->tiles_x * pl->tiles_y * nn;
     if (total <= 0) return true;
+    if (pb.in_dtype == PWS_F16)
+        return pl->inter ? launch_ba<__half, 3, true>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st)
+                         : launch_ba<__half, 3, false>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st);
+    if (pb.in_dtype == PWS_BF16)
+        return pl->inter ? launch_ba<__nv_bfloat16, 3, true>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st)
+                         : launch_ba<__nv_bfloat16, 3, false>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st);
     if (pb.g.C == 3)
-        return pl->inter ? launch_ba<3, true>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st)
-                         : launch_ba<3, false>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st);
-    return pl->inter ? launch_ba<1, true>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st)
-                     : launch_ba<1, false>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st);
+        return pl->inter ? launch_ba<float, 3, true>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st)
+                         : launch_ba<float, 3, false>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st);
+    return pl->inter ? launch_ba<float, 1, true>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st)
+                     : launch_ba<float, 1, false>(pl->tp, pb, pl->tiles_x, pl->tiles_y, total, n0, st);
 }
 
 }  // namespace pws

@@ -219,7 +219,7 @@ def test_backward_16bit_frames_fp32_maps(pw, dtype, pad, shape):
     frames, g, gout = make("smooth", N, C, H, W, H, W, False, "planar", seed=61)
     f16, go16 = frames.to(dtype), gout.to(dtype)
     gin, gg = pw.warp2d_backward(go16, f16, g, PAD[pad], False, (True, True))
-    assert last_kernel() == "bwd_lean_16"
+    assert last_kernel() == ("bwd_tma_16" if C == 3 else "bwd_lean_16")   # the 16-bit TMA backward has the RGB instantiations only
     assert gin.dtype == dtype and gg.dtype == torch.float32
     rin, rg = pw.warp2d_backward(go16.float(), f16.float(), g, PAD[pad], False, (True, True))
     assert torch.equal(gg, rg)
@@ -235,3 +235,32 @@ def test_backward_16bit_frames_fp32_maps(pw, dtype, pad, shape):
     out = pw.grid_sample(fa, ga, "bilinear", pad, False)
     out.backward(go16)
     assert fa.grad.dtype == dtype and torch.equal(ga.grad, gg)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+def test_tma_backward_16bit_layouts_masks_and_rough_maps(pw, dtype, pad):
+    # the persistent backward with 16-bit grad_output tiles and frame boxes (bwd_tma_16): every map kind, both align modes,
+    # planar and interleaved maps, partial tiles, each output mask -- against this library's fp32 path on the upcast inputs
+    # (grad_grid bit-exact: same arithmetic on the same values) and ATen (grad_input <= 1e-4, accumulated in fp32)
+    for shape in [(2, 3, 144, 256, 144, 256), (1, 3, 270, 480, 250, 392), (3, 3, 96, 200, 96, 200)]:   # (16-bit rows: widths in multiples of 8)
+        N, C, H, W, Ho, Wo = shape
+        for kind in ("smooth", "noisy", "random", "centre"):
+            for align in (False, True):
+                for layout in ("planar", "interleaved"):
+                    frames, g, gout = make(kind, N, C, H, W, Ho, Wo, align, layout, seed=71)
+                    f16, go16 = frames.to(dtype), gout.to(dtype)
+                    acc = torch.empty(f16.shape, dtype=torch.float32, device="cuda")
+                    _, gg = pw.warp2d_backward(go16, f16, g, PAD[pad], align, (True, True), grad_input=acc)
+                    assert last_kernel() == "bwd_tma_16"
+                    rin, rg = pw.warp2d_backward(go16.float(), f16.float(), g, PAD[pad], align, (True, True))
+                    assert last_kernel() == "bwd_tma"
+                    assert torch.equal(gg, rg)
+                    ain, _ = torch.ops.aten.grid_sampler_2d_backward(go16.float(), f16.float(), g, 0, PAD[pad], align, (True, False))
+                    scale = float(ain.abs().max())
+                    assert float((acc - ain).abs().max()) <= 1e-4 * scale
+                    acc1 = torch.full(f16.shape, 7.0, dtype=torch.float32, device="cuda")       # need not arrive zeroed
+                    pw.warp2d_backward(go16, f16, g, PAD[pad], align, (True, False), grad_input=acc1)
+                    assert float((acc1 - ain).abs().max()) <= 1e-4 * scale
+                    _, gg1 = pw.warp2d_backward(go16, f16, g, PAD[pad], align, (False, True))
+                    assert torch.equal(gg1, rg)

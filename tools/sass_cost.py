@@ -9,7 +9,7 @@ measured by tools/exp/exp_pipes.cu on B200 (FFMA / IADD = 1, IMAD / LOP3 = 1.4, 
 import os, re, subprocess, sys, collections
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 args = sys.argv[1] if len(sys.argv) > 1 else "3,0,0,0,1,1"
-key = "bwd_tma_kernelILi%sELb%sELb%sELb%sELb%sELb%sE" % tuple(args.split(","))
+key = "bwd_tma_kernelIfLi%sELb%sELb%sELb%sELb%sELb%sE" % tuple(args.split(","))   # the fp32 instantiation
 obj = "/tmp/sass_cost_bwd.o"
 subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-c",
                        os.environ.get("SASS_COST_SRC", os.path.join(root, "pwstablenet_b200/csrc/warp_bwd_tma.cu")), "-o", obj] + sys.argv[2:])
