@@ -33,19 +33,21 @@ def rot(x, y, deg):
     px, py = x * W / 2, y * H / 2
     return (c * px - s * py) * 0.98 / (W / 2), (s * px + c * py) * 0.98 / (H / 2)
 
-fr = torch.rand(N, C, H, W, device="cuda") * 255
-go = torch.rand(N, C, H, W, device="cuda")
+DT = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[os.environ.get("MAP_BENCH_DTYPE", "f32")]   # frames and grad_output
+fr = (torch.rand(N, C, H, W, device="cuda") * 255).to(DT)
+go = torch.rand(N, C, H, W, device="cuda").to(DT)
 K = 20
+GI = torch.empty(N, C, H, W, device="cuda", dtype=torch.float32)   # caller-provided fp32 grad_input: the kernel alone, no rounding pass
 for name, g in maps():
     row = []
     for mask in ((True, True), (True, False), (False, True)):
         for _ in range(3):
-            pw.warp2d_backward(go, fr, g, 0, False, mask)
+            pw.warp2d_backward(go, fr, g, 0, False, mask, grad_input=GI if mask[0] else None)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         s.record()
         for _ in range(K):
-            pw.warp2d_backward(go, fr, g, 0, False, mask)
+            pw.warp2d_backward(go, fr, g, 0, False, mask, grad_input=GI if mask[0] else None)
         e.record(); torch.cuda.synchronize()
         row.append(s.elapsed_time(e) / K)
     for _ in range(3):
