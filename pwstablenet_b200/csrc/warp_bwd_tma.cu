@@ -52,6 +52,9 @@ namespace {
 #ifndef PWS_BWD_VDUP
 #define PWS_BWD_VDUP 1
 #endif
+#ifndef PWS_BWD_SIDEWAYS   // broken parked sums find a home with the left neighbour / the own north-west tap instead of the queue
+#define PWS_BWD_SIDEWAYS 0
+#endif
 #ifndef PWS_BWD_GGRID_EXACT   // 1: grad_grid of interior tiles in ATen's statement order (bit-identical to it); 0: factored form --
 #define PWS_BWD_GGRID_EXACT 1 // 22 operations per pixel instead of 48, and not one microsecond faster: not the product
 #endif
@@ -625,9 +628,24 @@ __device__ __forceinline__ void interior_strip_fused(
             // (r > 0: nothing is parked in the strip's first row; the loop is unrolled, the test is free)
             const bool chain = r > 0 && co == o;                           // the parked south-west sum lands on this row's north-west tap
             const bool vdup = r > 0 && kVdup && co == o + W;        // ... on its south-west tap: same source row again
-            const bool broke = r > 0 && !chain && !vdup;
+            bool broke = r > 0 && !chain && !vdup;
             const bool e_chain = r > 0 && kEcarry && eo == o + 1, e_vdup = r > 0 && kEcarry && kVdup && eo == o + W + 1;
+#if PWS_BWD_SIDEWAYS
+            // Sideways homes for parked sums whose vertical chain broke (the map slants: a lane's column moved by one).
+            // (a) the parked south-east sum lands on this lane's OWN north-west tap: add it to the row's top, no entry;
+            // (b) the RIGHT neighbour's broken south-west sum lands on this lane's north-east or north-west tap: take it
+            //     (one shuffle of the target, one per channel) -- on the bench map 1.7 of a row's 8.8 queue entries
+            //     (tools/sim/straggler_homes.py).
+            const bool e_self = r > 0 && kEcarry && eo == o;
+            const int rco = __shfl_down_sync(0xffffffffu, broke ? co : -1, 1);
+            const bool r_ne = r > 0 && lane < 31 && rco == o + 1, r_nw = r > 0 && lane < 31 && rco == o;
+            // (the vote stands alone: behind `broke &&` only the lanes with a broken chain would execute it)
+            const unsigned taken = __ballot_sync(0xffffffffu, r_ne || r_nw) << 1;   // bit l: lane l's sum went to lane l - 1
+            if ((taken >> lane) & 1u) broke = false;
+            const bool e_broke = r > 0 && kEcarry && eo >= 0 && !e_chain && !e_vdup && !e_self;
+#else
             const bool e_broke = r > 0 && kEcarry && eo >= 0 && !e_chain && !e_vdup;
+#endif
             // (scalar: pairs would need as many register moves here as they save multiplies)
             const float nw = fmul(dw, dn), ne = fmul(de, dn), sw = fmul(dw, ds), se = fmul(de, ds);
             float et[CS], eb[CS], old_c[CS], old_e[CS];
@@ -638,6 +656,14 @@ __device__ __forceinline__ void interior_strip_fused(
                 old_e[k] = ev[k];
                 if (e_chain) et[k] += ev[k];                // parked south-east sum: this row's north-east tap
                 if (e_vdup) eb[k] += ev[k];
+#if PWS_BWD_SIDEWAYS
+                if (r > 0) {
+                    const float rv = __shfl_down_sync(0xffffffffu, cv[k], 1);   // the right neighbour's parked south-west sum
+                    if (r_ne) et[k] += rv;
+                    if (r_nw) top += rv;
+                    if (e_self) top += ev[k];
+                }
+#endif
                 const float pt = (PWS_KO & 32) ? et[k] : __shfl_up_sync(0xffffffffu, et[k], 1), pb = (PWS_KO & 32) ? eb[k] : __shfl_up_sync(0xffffffffu, eb[k], 1);
                 if (take) { top += pt; bot += pb; }
                 old_c[k] = cv[k];
