@@ -103,3 +103,25 @@ def test_compiled_torch_shim_loads_and_binds_the_same_library():
     maps = open("/proc/self/maps").read()
     assert maps.count(os.path.join("pwstablenet_b200", "libpwswarp.so")) > 0
     assert len({l.split()[-1] for l in maps.splitlines() if l.endswith("libpwswarp.so")}) == 1   # one copy, not two
+
+
+def test_aten_override_registers_for_cuda_only_and_uninstalls():
+    """install(aten_override=True) replaces the CUDA kernels of the two operators; CPU tensors keep ATen's CPU kernels, the
+    functional-level patch keeps refusing them, and uninstall() drops both."""
+    import torch.nn.functional as F
+    import pwstablenet_b200 as pw
+    from pwstablenet_b200 import functional
+    f, g = torch.rand(1, 1, 4, 4), torch.rand(1, 4, 4, 2) * 2 - 1
+    ref = torch.grid_sampler(f, g, 0, 0, False)
+    orig = F.grid_sample
+    pw.install(aten_override=True)
+    try:
+        assert functional._aten_lib is not None and F.grid_sample is pw.grid_sample
+        assert torch.equal(torch.grid_sampler(f, g, 0, 0, False), ref)       # CPU dispatch key untouched
+        with pytest.raises(RuntimeError, match="CUDA tensors only"):
+            F.grid_sample(f, g, align_corners=False)
+        pw.install(aten_override=True)                                        # idempotent
+    finally:
+        pw.uninstall()
+    assert functional._aten_lib is None and F.grid_sample is orig
+    assert torch.equal(torch.grid_sampler(f, g, 0, 0, False), ref)
